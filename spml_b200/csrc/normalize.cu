@@ -1,0 +1,307 @@
+// A8 front half: valid-pixel scan, NCHW -> packed NHWC rows with L2 normalisation and
+// location-feature concatenation (reference spml/utils/segsort/common.py:306-310,
+// 339-365), and its backward.  HBM-bound: every embedding element is read once
+// (coalesced along the pixel axis), transposed through shared memory and written
+// once (coalesced along the channel axis).
+#include "common.cuh"
+
+namespace spml {
+
+constexpr int kTile = 128;          // pixels per CTA (also the scan granularity)
+constexpr int kTileLd = kTile + 1;  // odd stride: conflict-free in both directions
+constexpr int kPackThreads = 256;
+
+__device__ __forceinline__ bool pixel_kept(const int64_t* labels, int has_ignore,
+                                           int64_t ignore_index, int64_t pix) {
+  return !has_ignore || labels[pix] != ignore_index;
+}
+
+// the ignore index may live on the device (generate_clusters passes labels.max() + 1)
+__device__ __forceinline__ int64_t resolve_ignore(int64_t host_value, const int64_t* dev_value) {
+  return dev_value ? *dev_value : host_value;
+}
+
+// Single-pass chained scan (decoupled look-back) over tiles of kTile pixels.
+// state[t] packs {flag:32 | value:32}; flag 1 = tile aggregate, 2 = inclusive prefix.
+__global__ void valid_scan_kernel(const int64_t* __restrict__ labels, int has_ignore,
+                                  int64_t ignore_host, const int64_t* __restrict__ ignore_dev,
+                                  int batch, int n, int tiles_per_img,
+                                  int32_t* __restrict__ dst, int32_t* __restrict__ src,
+                                  int32_t* __restrict__ img_off, unsigned long long* state,
+                                  int* ticket) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[kTile / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t ignore_index = has_ignore ? resolve_ignore(ignore_host, ignore_dev) : 0;
+  const int b = tile / tiles_per_img;
+  const int p = (tile % tiles_per_img) * kTile + threadIdx.x;
+  const int64_t pix = (int64_t)b * n + p;
+  const bool keep = p < n && pixel_kept(labels, has_ignore, ignore_index, pix);
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kTile / 32; ++w) {
+    if (w < warp) before += s_warp[w];
+    total += s_warp[w];
+  }
+  if (threadIdx.x == 0) {
+    int prefix = 0;
+    if (tile > 0) {
+      volatile unsigned long long* vs = state;
+      vs[tile] = (1ull << 32) | (unsigned)total;
+      int idx = tile - 1;
+      while (true) {
+        unsigned long long s = vs[idx];
+        const unsigned flag = (unsigned)(s >> 32);
+        if (flag == 0) continue;
+        prefix += (int)(unsigned)(s & 0xffffffffu);
+        if (flag == 2) break;
+        --idx;
+      }
+    }
+    __threadfence();
+    ((volatile unsigned long long*)state)[tile] = (2ull << 32) | (unsigned)(prefix + total);
+    s_prefix = prefix;
+    if (tile % tiles_per_img == 0) img_off[b] = prefix;
+    if (tile == batch * tiles_per_img - 1) img_off[batch] = prefix + total;
+  }
+  __syncthreads();
+  if (p < n) {
+    const int row = keep ? s_prefix + before + __popc(ballot & ((1u << lane) - 1)) : -1;
+    dst[pix] = row;
+    if (src && keep) src[row] = (int32_t)pix;
+  }
+}
+
+// emb [batch, dim, n] -> e [rows, dim], el [rows, dim+loc_ch]
+__global__ void __launch_bounds__(kPackThreads)
+normalize_pack_fwd_kernel(const float* __restrict__ emb, const float* __restrict__ loc,
+                          int64_t loc_batch_stride, int loc_ch,
+                          const int64_t* __restrict__ labels, const int64_t* __restrict__ seeds,
+                          int64_t seed_batch_stride, const int32_t* __restrict__ dst, int dim,
+                          int n, int tiles_per_img, int64_t batch_index_offset, float eps,
+                          float* __restrict__ e, float* __restrict__ el, float* __restrict__ nx,
+                          float* __restrict__ nc, int64_t* __restrict__ labels_out,
+                          int64_t* __restrict__ batch_out, int32_t* __restrict__ seed_out) {
+  extern __shared__ float tile[];  // [dim][kTileLd]
+  __shared__ float s_nx[kTile], s_nc[kTile];
+  __shared__ int s_row[kTile];
+  const int b = blockIdx.x / tiles_per_img;
+  const int p0 = (blockIdx.x % tiles_per_img) * kTile;
+  const int np = min(kTile, n - p0);
+  const int tid = threadIdx.x;
+  const int dp = dim + loc_ch;
+
+  if (tid < kTile) s_row[tid] = tid < np ? dst[(int64_t)b * n + p0 + tid] : -1;
+  {
+    const int px = tid % kTile;
+    for (int d = tid / kTile; d < dim; d += kPackThreads / kTile)
+      tile[d * kTileLd + px] = px < np ? emb[((int64_t)b * dim + d) * n + p0 + px] : 0.f;
+  }
+  __syncthreads();
+
+  if (tid < kTile) {
+    float ss = 0.f;
+    for (int d = 0; d < dim; ++d) {
+      const float v = tile[d * kTileLd + tid];
+      ss += v * v;
+    }
+    const float n1 = sqrtf(ss);
+    const bool ok1 = n1 >= eps;
+    const float div1 = ok1 ? n1 : eps;
+    float ss2 = 0.f;
+    for (int d = 0; d < dim; ++d) {
+      const float v = tile[d * kTileLd + tid] / div1;
+      tile[d * kTileLd + tid] = v;
+      ss2 += v * v;
+    }
+    if (tid < np) {
+      const float* lp = loc + (int64_t)b * loc_batch_stride + (int64_t)(p0 + tid) * loc_ch;
+      for (int c = 0; c < loc_ch; ++c) ss2 += lp[c] * lp[c];
+    }
+    const float n2 = sqrtf(ss2);
+    s_nx[tid] = ok1 ? n1 : -eps;
+    s_nc[tid] = n2 >= eps ? n2 : -eps;
+  }
+  __syncthreads();
+
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int px = warp; px < np; px += kPackThreads / 32) {
+    const int r = s_row[px];
+    if (r < 0) continue;
+    const float div2 = fabsf(s_nc[px]);
+    for (int d = lane; d < dim; d += 32) {
+      const float v = tile[d * kTileLd + px];
+      e[(int64_t)r * dim + d] = v;
+      el[(int64_t)r * dp + d] = v / div2;
+    }
+    const int64_t pix = (int64_t)b * n + p0 + px;
+    if (lane < loc_ch)
+      el[(int64_t)r * dp + dim + lane] =
+          loc[(int64_t)b * loc_batch_stride + (int64_t)(p0 + px) * loc_ch + lane] / div2;
+    if (lane == 0) {
+      nx[r] = s_nx[px];
+      nc[r] = s_nc[px];
+      if (labels_out) labels_out[r] = labels[pix];
+      if (batch_out) batch_out[r] = b + batch_index_offset;
+      if (seed_out) seed_out[r] = (int32_t)seeds[(int64_t)b * seed_batch_stride + p0 + px];
+    }
+  }
+}
+
+constexpr int kMaxPerLane = (SPML_MAX_DIM + 31) / 32;  // channel slots per lane
+
+// d(emb) from d(e), d(el).  One warp per pixel for the dot products, then a
+// transposed, pixel-coalesced store.
+__global__ void __launch_bounds__(kPackThreads)
+normalize_pack_bwd_kernel(const float* __restrict__ de, const float* __restrict__ del,
+                          const float* __restrict__ e, const float* __restrict__ el,
+                          const float* __restrict__ nx, const float* __restrict__ nc,
+                          const int32_t* __restrict__ dst, int dim, int loc_ch, int n,
+                          int tiles_per_img, float eps, float* __restrict__ demb) {
+  extern __shared__ float tile[];  // [dim][kTileLd]
+  const int b = blockIdx.x / tiles_per_img;
+  const int p0 = (blockIdx.x % tiles_per_img) * kTile;
+  const int np = min(kTile, n - p0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dp = dim + loc_ch;
+
+  for (int px = warp; px < np; px += kPackThreads / 32) {
+    const int r = dst[(int64_t)b * n + p0 + px];
+    float g[kMaxPerLane], ev[kMaxPerLane];
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) g[s] = 0.f, ev[s] = 0.f;
+    if (r >= 0) {
+      // through el = cat(e, loc) / max(||cat||, eps)
+      if (del) {
+        float t1 = 0.f;
+        for (int d = lane; d < dp; d += 32) t1 += el[(int64_t)r * dp + d] * del[(int64_t)r * dp + d];
+        t1 = warp_sum(t1);
+        const float n2 = nc[r];
+#pragma unroll
+        for (int s = 0; s < kMaxPerLane; ++s) {
+          const int d = lane + 32 * s;
+          if (d < dim) {
+            const float gl = del[(int64_t)r * dp + d];
+            g[s] = n2 > 0.f ? (gl - el[(int64_t)r * dp + d] * t1) / n2 : gl / eps;
+          }
+        }
+      }
+      float t2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxPerLane; ++s) {
+        const int d = lane + 32 * s;
+        if (d < dim) {
+          if (de) g[s] += de[(int64_t)r * dim + d];
+          ev[s] = e[(int64_t)r * dim + d];
+          t2 += ev[s] * g[s];
+        }
+      }
+      t2 = warp_sum(t2);
+      const float n1 = nx[r];
+#pragma unroll
+      for (int s = 0; s < kMaxPerLane; ++s)
+        g[s] = n1 > 0.f ? (g[s] - ev[s] * t2) / n1 : g[s] / eps;
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      const int d = lane + 32 * s;
+      if (d < dim) tile[d * kTileLd + px] = g[s];
+    }
+  }
+  __syncthreads();
+  const int px = tid % kTile;
+  if (px < np)
+    for (int d = tid / kTile; d < dim; d += kPackThreads / kTile)
+      demb[((int64_t)b * dim + d) * n + p0 + px] = tile[d * kTileLd + px];
+}
+
+static int tiles_per_image(int n) { return (int)ceil_div(n, kTile); }
+
+}  // namespace spml
+
+extern "C" {
+
+size_t spml_valid_scan_workspace_bytes(int batch, int n) {
+  if (batch <= 0 || n <= 0) return 16;
+  const size_t tiles = (size_t)batch * spml::tiles_per_image(n);
+  return 16 + tiles * sizeof(unsigned long long);
+}
+
+int spml_valid_scan(const int64_t* labels, int has_ignore, int64_t ignore_index,
+                    const int64_t* ignore_index_dev, int batch, int n, int32_t* dst, int32_t* src, int32_t* img_off, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  SPML_CHECK_ARG(batch > 0 && n > 0 && dst && img_off && workspace,
+                 "valid_scan: bad arguments");
+  SPML_CHECK_ARG(!has_ignore || labels, "valid_scan: labels required with an ignore index");
+  SPML_CHECK_SUPPORTED((int64_t)batch * n < (1ll << 31), "valid_scan: more than 2^31 pixels");
+  const size_t need = spml_valid_scan_workspace_bytes(batch, n);
+  if (workspace_bytes < need) {
+    spml::set_error("valid_scan: workspace %zu < %zu bytes", workspace_bytes, need);
+    return SPML_E_WORKSPACE;
+  }
+  cudaStream_t st = spml::as_stream(stream);
+  const int tpi = spml::tiles_per_image(n);
+  SPML_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  int* ticket = reinterpret_cast<int*>(workspace);
+  unsigned long long* state =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16);
+  spml::valid_scan_kernel<<<batch * tpi, spml::kTile, 0, st>>>(
+      labels, has_ignore, ignore_index, ignore_index_dev, batch, n, tpi, dst, src, img_off, state,
+      ticket);
+  SPML_LAUNCH_CHECK("valid_scan_kernel");
+  return SPML_OK;
+}
+
+int spml_normalize_pack_fwd(const float* emb, const float* loc, int64_t loc_batch_stride,
+                            int loc_ch, const int64_t* labels, const int64_t* seeds,
+                            int64_t seed_batch_stride, const int32_t* dst, int batch, int dim,
+                            int n, int64_t batch_index_offset, float eps, float* e, float* el,
+                            float* nx, float* nc, int64_t* labels_out, int64_t* batch_out,
+                            int32_t* seed_out, void* stream) {
+  SPML_CHECK_ARG(emb && dst && e && el && nx && nc && batch > 0 && n > 0 && dim > 0,
+                 "normalize_pack_fwd: bad arguments");
+  SPML_CHECK_ARG(loc_ch == 0 || loc, "normalize_pack_fwd: loc required when loc_ch > 0");
+  SPML_CHECK_ARG(!labels_out || labels, "normalize_pack_fwd: labels_out needs labels");
+  SPML_CHECK_ARG(!seed_out || seeds, "normalize_pack_fwd: seed_out needs seeds");
+  SPML_CHECK_SUPPORTED(loc_ch >= 0 && loc_ch <= 32 && dim + loc_ch <= SPML_MAX_DIM,
+                       "normalize_pack_fwd: dim %d + loc_ch %d exceeds %d", dim, loc_ch,
+                       SPML_MAX_DIM);
+  const size_t smem = (size_t)dim * spml::kTileLd * sizeof(float);
+  SPML_CUDA(cudaFuncSetAttribute(spml::normalize_pack_fwd_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tpi = spml::tiles_per_image(n);
+  spml::normalize_pack_fwd_kernel<<<batch * tpi, spml::kPackThreads, smem,
+                                    spml::as_stream(stream)>>>(
+      emb, loc, loc_batch_stride, loc_ch, labels, seeds, seed_batch_stride, dst, dim, n, tpi,
+      batch_index_offset, eps, e, el, nx, nc, labels_out, batch_out, seed_out);
+  SPML_LAUNCH_CHECK("normalize_pack_fwd_kernel");
+  return SPML_OK;
+}
+
+int spml_normalize_pack_bwd(const float* de, const float* del, const float* e, const float* el,
+                            const float* nx, const float* nc, const int32_t* dst, int batch,
+                            int dim, int loc_ch, int n, float eps, float* demb, void* stream) {
+  SPML_CHECK_ARG(e && el && nx && nc && dst && demb && batch > 0 && n > 0 && dim > 0,
+                 "normalize_pack_bwd: bad arguments");
+  SPML_CHECK_SUPPORTED(loc_ch >= 0 && dim + loc_ch <= SPML_MAX_DIM,
+                       "normalize_pack_bwd: dim %d + loc_ch %d exceeds %d", dim, loc_ch,
+                       SPML_MAX_DIM);
+  const size_t smem = (size_t)dim * spml::kTileLd * sizeof(float);
+  SPML_CUDA(cudaFuncSetAttribute(spml::normalize_pack_bwd_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tpi = spml::tiles_per_image(n);
+  spml::normalize_pack_bwd_kernel<<<batch * tpi, spml::kPackThreads, smem,
+                                    spml::as_stream(stream)>>>(
+      de, del, e, el, nx, nc, dst, dim, loc_ch, n, tpi, eps, demb);
+  SPML_LAUNCH_CHECK("normalize_pack_bwd_kernel");
+  return SPML_OK;
+}
+
+}  // extern "C"

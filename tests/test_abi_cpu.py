@@ -1,0 +1,71 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header
+declares, the ctypes table covers the header, and the product refuses CPU tensors
+(no fallback).  No kernel runs here."""
+
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from conftest import ROOT
+from spml_b200 import _lib
+
+
+def header_functions():
+  text = open(os.path.join(ROOT, 'include', 'spml_b200.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(spml_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+  names = header_functions()
+  assert len(names) >= 20
+  lib = _lib.load()
+  for n in names:
+    assert hasattr(lib, n), 'not exported: ' + n
+  assert sorted(_lib.SIGNATURES) == names
+  out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True,
+                       text=True).stdout
+  exported = set(re.findall(r' T (spml_[a-z0-9_]+)', out))
+  assert set(names) <= exported
+
+
+def test_abi_version_and_error_text():
+  lib = _lib.load()
+  assert lib.spml_abi_version() == _lib.ABI_VERSION
+  assert lib.spml_unique_inverse(None, None, -1, None, 0, None, None, None, None, None, None,
+                                 0, None) == -1
+  assert b'unique_inverse' in lib.spml_last_error()
+
+
+def test_desc_layout_matches_c():
+  """sizeof(spml_segsort_desc) as the compiler sees it."""
+  src = '#include "spml_b200.h"\n#include <stdio.h>\nint main(){printf("%zu",sizeof(spml_segsort_desc));}'
+  exe = '/tmp/spml_desc_size'
+  r = subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe],
+                     input=src, text=True, capture_output=True)
+  assert r.returncode == 0, r.stderr
+  import ctypes
+  assert int(subprocess.run([exe], capture_output=True, text=True).stdout) == ctypes.sizeof(
+      _lib.SegsortDesc)
+
+
+def test_no_cpu_fallback():
+  from spml_b200 import general_common, segsort_common, segsort_loss
+  with pytest.raises(RuntimeError, match='CUDA'):
+    general_common.normalize_embedding(torch.zeros(2, 3))
+  with pytest.raises(RuntimeError, match='CUDA'):
+    segsort_common.segment_by_kmeans(torch.zeros(1, 4, 8, 8))
+  with pytest.raises(RuntimeError, match='CUDA'):
+    segsort_loss.SegSortLoss(10)(torch.zeros(4, 3), torch.zeros(4, dtype=torch.long),
+                                 torch.zeros(4, dtype=torch.long), torch.zeros(2, 3),
+                                 torch.zeros(2, dtype=torch.long))
+
+
+def test_product_does_not_import_oracle():
+  pkg = os.path.join(ROOT, 'spml_b200')
+  for fn in os.listdir(pkg):
+    if fn.endswith('.py'):
+      assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn

@@ -1,0 +1,217 @@
+"""GPU parity tests of the individual operators (reference-named API) against the
+golden unit vectors made by the reference and against the CPU oracle."""
+
+import ctypes
+
+import pytest
+import torch
+
+from helpers import norm_err
+from oracle import spml_oracle as O
+from spml_b200 import _lib, general_common, model_utils, ops, segsort_common, segsort_eval
+from spml_b200 import segsort_loss, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(t):
+  return t.cuda()
+
+
+def close(a, b, tol=2e-6):
+  a = a.cpu()
+  assert a.shape == b.shape, (a.shape, b.shape)
+  err = float((a - b).abs().max()) if a.numel() else 0.0
+  assert err <= tol, err
+
+
+def test_normalize_embedding(units):
+  u = units['normalize']
+  x = cu(u['x']).requires_grad_(True)
+  y = general_common.normalize_embedding(x)
+  close(y.detach(), u['y'], 1e-7)
+  g = torch.randn(u['x'].shape, generator=torch.Generator().manual_seed(1))
+  y.backward(cu(g))
+  xr = u['x'].clone().requires_grad_(True)
+  O.l2_normalize(xr).backward(g)
+  rows = [0, 1, 3, 5]          # rows 2 / 4 sit on the clamped branch (scale 1e12)
+  close(x.grad.cpu()[rows], xr.grad[rows], 1e-5)
+  assert torch.allclose(x.grad.cpu()[[2, 4]], xr.grad[[2, 4]], rtol=1e-5)
+
+
+def test_prototypes_from_labels(units):
+  u = units['prototypes']
+  close(segsort_common.calculate_prototypes_from_labels(cu(u['e']), cu(u['lab']), 6), u['p'])
+  close(segsort_common.calculate_prototypes_from_labels(cu(u['e']), cu(u['lab'])), u['p_auto'])
+
+
+def test_prototype_backward_matches_autograd():
+  g = torch.Generator().manual_seed(3)
+  e = O.l2_normalize(torch.randn(500, 66, generator=g))
+  seg = torch.randint(0, 17, (500,), generator=g)
+  w = torch.randn(19, 66, generator=g)
+  er = e.clone().requires_grad_(True)
+  (O.prototypes_from_labels(er, seg, 19) * w).sum().backward()
+  ec = cu(e).requires_grad_(True)
+  (segsort_common.calculate_prototypes_from_labels(ec, cu(seg), 19) * cu(w)).sum().backward()
+  assert norm_err(ec.grad.cpu(), er.grad) < 1e-5
+
+
+def test_nearest_prototype_ties(units):
+  t = units['nearest_ties']
+  got = segsort_common.find_nearest_prototypes(cu(t['e']), cu(t['p'])).cpu()
+  assert torch.equal(got, t['idx'])
+
+
+def test_kmeans_with_empty_cluster(units):
+  u = units['kmeans_empty']
+  got = segsort_common.kmeans_with_initial_labels(cu(u['e']), cu(u['lab0']), 4, 10).cpu()
+  assert torch.equal(got, u['lab'])
+
+
+@pytest.mark.parametrize('n,dim,k', [(5000, 66, 36), (3000, 37, 144), (4097, 130, 100)])
+def test_kmeans_matches_oracle(n, dim, k):
+  g = torch.Generator().manual_seed(n + dim)
+  centres = torch.randn(k, dim, generator=g)
+  cell = torch.arange(n) * k // n
+  e = O.l2_normalize(centres[cell] + 0.7 * torch.randn(n, dim, generator=g))
+  lab0 = cell[torch.randperm(n, generator=g)]
+  want = O.spherical_kmeans(e, lab0, k, 10)
+  got = segsort_common.kmeans_with_initial_labels(cu(e), cu(lab0), k, 10).cpu()
+  assert int((got != want).sum()) == 0
+
+
+def test_prepare_prototype_labels(units):
+  u = units['prototype_labels']
+  plab, inv = segsort_common.prepare_prototype_labels(cu(u['sem']), cu(u['inst']), 256)
+  assert torch.equal(plab.cpu(), u['plab']) and torch.equal(inv.cpu(), u['inv'])
+
+
+def test_unique_inverse_random():
+  g = torch.Generator().manual_seed(9)
+  for n, hi_max, lo_max in ((1, 1, 1), (1000, 7, 50), (70000, 300, 2000), (257, 1, 100000)):
+    hi = torch.randint(0, hi_max, (n,), generator=g)
+    lo = torch.randint(0, lo_max, (n,), generator=g)
+    keys, inv = torch.unique(hi * (lo.max() + 1) + lo, return_inverse=True)
+    got_inv, uhi, ulo, count, bound = ops.unique_inverse(cu(lo), hi=cu(hi), bound=0)
+    m = int(count)
+    assert m == keys.numel() and int(bound) == int(lo.max()) + 1
+    assert torch.equal(got_inv.cpu(), inv)
+    assert torch.equal((uhi[:m] * bound + ulo[:m]).cpu(), keys)
+
+
+def test_segsort_loss(units):
+  u = units['segsort']
+  e = cu(u['e']).requires_grad_(True)
+  p = cu(u['p']).requires_grad_(True)
+  loss = segsort_loss.SegSortLoss(u['kappa'])(e, cu(u['sem']), cu(u['seg']), p, cu(u['psem']))
+  loss.backward()
+  assert abs(float(loss) - float(u['loss'])) <= 1e-5 * abs(float(u['loss']))
+  assert norm_err(e.grad.cpu(), u['de']) < 1e-4
+  assert norm_err(p.grad.cpu(), u['dp']) < 1e-4
+
+
+def test_set_segsort_loss(units):
+  u = units['set_segsort']
+  e = cu(u['e']).requires_grad_(True)
+  p = cu(u['p']).requires_grad_(True)
+  loss = segsort_loss.SetSegSortLoss(u['kappa'])(e, cu(u['tags']), cu(u['seg']), p,
+                                                cu(u['ptags']))
+  loss.backward()
+  assert abs(float(loss) - float(u['loss'])) <= 1e-5 * abs(float(u['loss']))
+  assert norm_err(e.grad.cpu(), u['de']) < 1e-4
+  assert norm_err(p.grad.cpu(), u['dp']) < 1e-4
+
+
+@pytest.mark.parametrize('n,m,dim,kappa', [(1000, 200, 64, 6.0), (777, 65, 66, 16.0),
+                                           (300, 1500, 130, 12.0), (129, 3, 37, 10.0)])
+def test_segsort_loss_random(n, m, dim, kappa):
+  g = torch.Generator().manual_seed(n * 7 + m)
+  protos = O.l2_normalize(torch.randn(m, dim, generator=g))
+  seg = torch.randint(0, m, (n,), generator=g)
+  psem = torch.randint(0, 5, (m,), generator=g)
+  e = O.l2_normalize(protos[seg] + 0.5 * torch.randn(n, dim, generator=g))
+  er, pr = e.clone().requires_grad_(True), protos.clone().requires_grad_(True)
+  want = O.segsort_loss(er.double(), psem[seg], seg, pr.double(), psem, kappa)
+  want.backward()
+  ec, pc = cu(e).requires_grad_(True), cu(protos).requires_grad_(True)
+  got = segsort_loss.SegSortLoss(kappa)(ec, cu(psem[seg]), cu(seg), pc, cu(psem))
+  got.backward()
+  assert abs(float(got) - float(want)) <= 2e-5 * abs(float(want))
+  assert norm_err(ec.grad.cpu(), er.grad) < 1e-4
+  assert norm_err(pc.grad.cpu(), pr.grad) < 1e-4
+
+
+def test_topk(units):
+  u = units['topk']
+  acc, lab = segsort_eval.top_k_ranking(cu(u['q']), cu(u['ql']), cu(u['p']), cu(u['pl']), 5)
+  assert torch.equal(lab.cpu(), u['labels'])
+  assert abs(float(acc) - float(u['acc'])) < 1e-6
+  maj = segsort_eval.majority_label_from_topk(lab, 3)
+  assert torch.equal(maj.cpu(), u['majority'])
+
+
+def test_topk_large_k20():
+  g = torch.Generator().manual_seed(11)
+  q = O.l2_normalize(torch.randn(333, 64, generator=g))
+  p = O.l2_normalize(torch.randn(5000, 64, generator=g))
+  ql, pl = torch.randint(0, 21, (333,), generator=g), torch.randint(0, 21, (5000,), generator=g)
+  acc_w, lab_w = O.top_k_ranking(q, ql, p, pl, 20)
+  acc, lab = segsort_eval.top_k_ranking(cu(q), cu(ql), cu(p), cu(pl), 20)
+  assert float((lab.cpu() != lab_w).float().mean()) < 1e-3    # near-ties may swap
+  assert abs(float(acc) - float(acc_w)) < 1e-3
+
+
+def test_segment_by_kmeans_edges(units):
+  u = units['segment_ignore_image']
+  got = segsort_common.segment_by_kmeans(cu(u['emb']), cu(u['labels']), [2, 2], ignore_index=7,
+                                         iterations=3)
+  for a, k in zip(got, ('ce', 'cel', 'cl', 'ci', 'cb')):
+    if a.is_floating_point():
+      close(a.detach(), u[k])
+    else:
+      assert torch.equal(a.cpu(), u[k]), k
+  u = units['segment_user_clusters']
+  got = segsort_common.segment_by_kmeans(cu(u['emb']), cu(u['labels']), [2, 2],
+                                         cluster_indices=cu(u['cmap']), iterations=2)
+  for a, k in zip(got, ('ce', 'cel', 'cl', 'ci', 'cb')):
+    if a.is_floating_point():
+      close(a.detach(), u[k])
+    else:
+      assert torch.equal(a.cpu(), u[k]), k
+
+
+def test_gather_generic_path_equals_fast_path():
+  """gather_clustering_and_update_prototypes: the re-numbering path of
+  models/utils.py:95-108 and the shortcut for ids fresh from segment_by_kmeans."""
+  w = synth.WORKLOADS['small']
+  b = {k: v.cuda() for k, v in synth.make_batch(w).items()}
+  from spml_b200.head import generate_clusters
+  d = generate_clusters(b['embedding'], b['semantic_label'], b['instance_label'],
+                        b['local_feature'], w.label_divisor, w.ignore_index,
+                        list(w.num_clusters), w.iterations)
+  args = ([d['cluster_embedding']], [d['cluster_embedding_with_loc']], [d['cluster_index']],
+          [d['cluster_batch_index']], [d['cluster_semantic_label']],
+          [d['cluster_instance_label']])
+  fast = model_utils.gather_clustering_and_update_prototypes(*args)
+  plain = d['cluster_index'].clone()          # a copy carries no _spml_meta
+  args = (args[0], args[1], [plain]) + args[3:]
+  slow = model_utils.gather_clustering_and_update_prototypes(*args)
+  for a, c in zip(fast, slow):
+    assert torch.equal(a[0], c[0])
+  # two "devices" (lists of two): the reference's multi-GPU gather semantics
+  half = d['cluster_index'].shape[0] // 2
+  two = [[t[0][:half], t[0][half:]] for t in args]
+  multi = model_utils.gather_clustering_and_update_prototypes(*two)
+  assert torch.equal(torch.cat(multi[5]), slow[5][0]) and torch.equal(multi[0][0], slow[0][0])
+
+
+def test_abi_rejects_bad_arguments():
+  lib = _lib.load()
+  rc = lib.spml_segment_prototypes_fwd(None, 10, 8, None, 4, 1e-12, None, None, None, 0, None)
+  assert rc == -1 and b'null' in lib.spml_last_error()
+  x = torch.zeros(4, 200, device='cuda')
+  with pytest.raises(RuntimeError, match='exceeds'):
+    ops.nearest_prototype(x, x)
+  with pytest.raises(RuntimeError, match='CUDA'):
+    general_common.normalize_embedding(torch.zeros(3, 4))
