@@ -11,8 +11,12 @@
 // Math: SURVEY.md section 7.3 (checked against the reference's autograd).
 #include <math.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
+#include "segsort_tc.h"
 #include "tile_gemm.cuh"
 
 namespace spml {
@@ -494,6 +498,21 @@ static int check_desc(const spml_segsort_desc* d, const char* who) {
   return SPML_OK;
 }
 
+// desc.reserved: bit 0 forces the fp32 CUDA-core path, bit 1 forces the tensor-core path
+// (tests compare the two); otherwise the tensor-core path runs whenever it supports the
+// problem.  SPML_B200_SEGSORT=fp32|tc overrides the default.
+static bool use_tc_path(const spml_segsort_desc& d) {
+  if (!segsort_tc_supported(d)) return false;
+  if (d.reserved & 1) return false;
+  if (d.reserved & 2) return true;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("SPML_B200_SEGSORT");
+    env = !e ? 0 : (!strcmp(e, "fp32") ? 1 : (!strcmp(e, "tc") ? 2 : 0));
+  }
+  return env != 1;
+}
+
 template <typename Kernel>
 static int set_smem(Kernel k, size_t bytes, const char* who) {
   if (bytes > 227 * 1024) {
@@ -512,7 +531,9 @@ size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
   if (!d) return 0;
   const size_t fwd = (size_t)d->num_groups * spml::tiles_x_of(*d) * sizeof(float);
   const size_t bwd = (size_t)spml::proto_chunks_of(*d) * d->m * d->dim * sizeof(float);
-  return 16 + (fwd > bwd ? fwd : bwd);
+  size_t need = 16 + (fwd > bwd ? fwd : bwd);
+  if (spml::segsort_tc_supported(*d)) need = std::max(need, spml::segsort_tc_plan(*d, nullptr).bytes);
+  return need;
 }
 
 int spml_segsort_fwd(const spml_segsort_desc* d, float* stats, float* nll, float* loss,
@@ -529,6 +550,14 @@ int spml_segsort_fwd(const spml_segsort_desc* d, float* stats, float* nll, float
   cudaStream_t st = as_stream(stream);
   const int dpad = pad4(d->dim);
   const int tiles_x = tiles_x_of(*d);
+  if (use_tc_path(*d)) {
+    const TcPlan plan = segsort_tc_plan(*d, workspace);
+    rc = segsort_fwd_tc(*d, plan, stats, nll, st);
+    if (rc != SPML_OK) return rc;
+    segsort_loss_finalize_kernel<<<1, 32, 0, st>>>(*d, plan.partial, tiles_x, loss);
+    SPML_LAUNCH_CHECK("segsort_loss_finalize_kernel");
+    return SPML_OK;
+  }
   float* partial = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)dpad * (LDA + LDB) * sizeof(float);
   rc = set_smem(segsort_fwd_kernel, smem, "segsort_fwd");

@@ -1,0 +1,494 @@
+// C1 / C2 on the 5th-generation tensor cores: SegSort / SetSegSort forward as a
+// TMA-fed tcgen05 GEMM with the exp / label-mask / row-sum epilogue read straight out
+// of TMEM (reference spml/utils/segsort/loss.py:15-130; math in SURVEY.md 7.3).
+//
+// Precision: the fp32 unit vectors are split into bf16 hi + lo parts by a pre-pass and
+// every 16-wide K step issues three MMAs (hi.hi + lo.hi + hi.lo, fp32 accumulation in
+// TMEM), which keeps ~16 mantissa bits per product: cosines are exact to ~1e-5, inside
+// the 1e-3 parity bar with two orders of margin, at 3/1 of the bf16 MMA cost.
+//
+// Kernel layout (one CTA per 128-row tile, 10 warps):
+//   warp 0      TMA producer: A tile (all K blocks, hi + lo) once, then the prototype
+//               bank streamed in 128-column tiles through a 2-stage shared-memory ring
+//   warp 1      TMEM allocator and single-thread MMA issuer; accumulators double-buffered
+//               in TMEM (2 x 128 columns) so the epilogue of tile j overlaps the MMAs of j+1
+//   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns, ex2, code compare, running
+//               same / diff / self sums per row; two warps share each TMEM sub-partition
+//               (one per 64-column half)
+#include <math.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+#include "segsort_tc.h"
+
+namespace spml {
+
+// ------------------------------------------------------------------------- host: tensor map
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault,
+                                         &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                            uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SPML_E_CUDA;
+  }
+  const cuuint64_t gdim[2] = {inner, rows};
+  const cuuint64_t gstride[1] = {row_pitch_bytes};
+  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): inner %llu rows %llu pitch %llu", (int)r,
+              (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)row_pitch_bytes);
+    return SPML_E_CUDA;
+  }
+  return SPML_OK;
+}
+
+// ------------------------------------------------------------------------- pre-pass kernels
+
+// compact list of the valid prototype columns (sem_ann's labelled-prototype filter):
+// dst[c] = compact index or -1, src[k] = original column, *count = number kept.
+__global__ void compact_cols_kernel(const uint8_t* __restrict__ valid, int m,
+                                    int32_t* __restrict__ dst, int32_t* __restrict__ src,
+                                    int32_t* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < m; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    const bool keep = c < m && valid[c] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      if (w < warp) before += s_warp[w];
+      total += s_warp[w];
+    }
+    const int base = s_base;
+    if (c < m) {
+      const int k = keep ? base + before + __popc(ballot & ((1u << lane) - 1)) : -1;
+      dst[c] = k;
+      if (keep) src[k] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_base;
+}
+
+__device__ __forceinline__ void split_store(float x, float y, __nv_bfloat16* hi,
+                                            __nv_bfloat16* lo, int64_t at) {
+  const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+  const __nv_bfloat16 xl = __float2bfloat16_rn(x - __bfloat162float(xh));
+  const __nv_bfloat16 yl = __float2bfloat16_rn(y - __bfloat162float(yh));
+  *reinterpret_cast<__nv_bfloat162*>(hi + at) = __halves2bfloat162(xh, yh);
+  *reinterpret_cast<__nv_bfloat162*>(lo + at) = __halves2bfloat162(xl, yl);
+}
+
+// one warp per problem row: gather, split into bf16 hi / lo (zero padded to dp columns),
+// narrow the labels to int32 and translate the segment id to a compact column.
+__global__ void split_rows_kernel(const float* __restrict__ x, int64_t ld, int dim, int dp,
+                                  const int32_t* __restrict__ row_index,
+                                  const int32_t* __restrict__ group_off, int num_groups,
+                                  int64_t n_rows, const int64_t* __restrict__ pix_code,
+                                  const int64_t* __restrict__ seg,
+                                  const int32_t* __restrict__ col_dst, int64_t m,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  int32_t* __restrict__ rcode, int32_t* __restrict__ rseg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t live = group_off ? (int64_t)group_off[num_groups] : n_rows;
+  if (r >= live || r >= n_rows) return;
+  const int64_t orig = row_index ? (int64_t)row_index[r] : r;
+  const float* xr = x + orig * ld;
+  for (int q = lane * 2; q < dp; q += 64) {
+    const float a = q < dim ? xr[q] : 0.f;
+    const float b = q + 1 < dim ? xr[q + 1] : 0.f;
+    split_store(a, b, hi, lo, r * dp + q);
+  }
+  if (lane == 0) {
+    rcode[r] = (int32_t)pix_code[orig];
+    const int64_t s = seg[orig];
+    int32_t col = -1;
+    if (s >= 0 && s < m) col = col_dst ? col_dst[s] : (int32_t)s;
+    rseg[r] = col;
+  }
+}
+
+__global__ void split_protos_kernel(const float* __restrict__ p, int64_t ld, int dim, int dp,
+                                    const int32_t* __restrict__ col_src,
+                                    const int32_t* __restrict__ col_count, int64_t m,
+                                    const int64_t* __restrict__ proto_code,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    int32_t* __restrict__ ccode) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t live = col_count ? (int64_t)*col_count : m;
+  if (k >= live || k >= m) return;
+  const int64_t orig = col_src ? (int64_t)col_src[k] : k;
+  const float* pr = p + orig * ld;
+  for (int q = lane * 2; q < dp; q += 64) {
+    const float a = q < dim ? pr[q] : 0.f;
+    const float b = q + 1 < dim ? pr[q + 1] : 0.f;
+    split_store(a, b, hi, lo, k * dp + q);
+  }
+  if (lane == 0) ccode[k] = (int32_t)proto_code[orig];
+}
+
+// ------------------------------------------------------------------------- forward kernel
+
+constexpr int kTcBM = 128;          // rows per CTA = UMMA M
+constexpr int kTcBN = 128;          // prototype columns per tile = UMMA N
+constexpr int kTcThreads = 320;     // producer + MMA + 8 epilogue warps
+constexpr int kTcEpiThreads = 256;
+constexpr int kKBlockBytesA = kTcBM * 128;  // one 64-wide K block of the A tile (bf16)
+constexpr int kKBlockBytesB = kTcBN * 128;
+
+struct TcFwdArgs {
+  const int32_t* group_off;   // [num_groups + 1] or nullptr
+  const int32_t* col_off;     // [num_groups + 1] or nullptr
+  const int32_t* col_count;   // compact column count (proto_valid) or nullptr
+  int64_t n_rows;
+  int64_t m;
+  const int32_t* rcode;
+  const int32_t* rseg;
+  const int32_t* ccode;
+  float* stats;
+  float* nll;
+  float* partial;
+  float kappa_log2e;
+  int mode;
+  int nkb;       // 64-wide K blocks
+  int ksteps;    // 16-wide K steps
+  int stages;    // B ring depth (1 or 2)
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
+                      const __grid_constant__ CUtensorMap map_el,
+                      const __grid_constant__ CUtensorMap map_ph,
+                      const __grid_constant__ CUtensorMap map_pl, const TcFwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
+      bar_t_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int32_t s_ccode[2][kTcBN];
+  __shared__ float s_part[kTcBM][3];
+  __shared__ float s_nll[kTcBM];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.y;
+  const int64_t r_begin = a.group_off ? a.group_off[g] : 0;
+  const int64_t r_end = a.group_off ? a.group_off[g + 1] : a.n_rows;
+  const int64_t row0 = r_begin + (int64_t)blockIdx.x * kTcBM;
+  float* my_partial = a.partial + (size_t)g * gridDim.x + blockIdx.x;
+  if (row0 >= r_end) {
+    if (tid == 0) *my_partial = 0.f;
+    return;
+  }
+  const int rows = (int)min((int64_t)kTcBM, r_end - row0);
+  const int c_begin = a.col_off ? a.col_off[g] : 0;
+  const int c_end = a.col_count ? *a.col_count : (a.col_off ? a.col_off[g + 1] : (int)a.m);
+  const int ntiles = c_end > c_begin ? (c_end - c_begin + kTcBN - 1) / kTcBN : 0;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = smem;                                   // [nkb][128 x 128 B]
+  uint8_t* a_lo = smem + (size_t)a.nkb * kKBlockBytesA;
+  uint8_t* b_ring = smem + (size_t)2 * a.nkb * kKBlockBytesA;
+  const uint32_t stage_bytes = 2u * a.nkb * kKBlockBytesB;  // hi blocks then lo blocks
+
+  if (warp == 0 && lane == 0) {
+    tc::mbar_init(&bar_a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_b_full[s], 1);
+      tc::mbar_init(&bar_b_empty[s], 1);
+      tc::mbar_init(&bar_t_full[s], 1);
+      tc::mbar_init(&bar_t_empty[s], kTcEpiThreads / 32);
+    }
+    tc::fence_barrier_init();
+    tc::prefetch_tensormap(&map_eh);
+    tc::prefetch_tensormap(&map_el);
+    tc::prefetch_tensormap(&map_ph);
+    tc::prefetch_tensormap(&map_pl);
+  }
+  if (warp == 1) tc::tmem_alloc(&s_tmem_base, 2 * kTcBN);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      tc::mbar_expect_tx(&bar_a_full, 2u * a.nkb * kKBlockBytesA);
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        tc::tma_load_2d(&map_eh, &bar_a_full, a_hi + (size_t)kb * kKBlockBytesA, kb * 64,
+                        (int32_t)row0);
+        tc::tma_load_2d(&map_el, &bar_a_full, a_lo + (size_t)kb * kKBlockBytesA, kb * 64,
+                        (int32_t)row0);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % a.stages, use = j / a.stages;
+        tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);
+        tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
+        uint8_t* bh = b_ring + (size_t)s * stage_bytes;
+        uint8_t* bl = bh + (size_t)a.nkb * kKBlockBytesB;
+        const int32_t c0 = c_begin + j * kTcBN;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          tc::tma_load_2d(&map_ph, &bar_b_full[s], bh + (size_t)kb * kKBlockBytesB, kb * 64, c0);
+          tc::tma_load_2d(&map_pl, &bar_b_full[s], bl + (size_t)kb * kKBlockBytesB, kb * 64, c0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(kTcBM, kTcBN, 0, 0);
+      tc::mbar_wait(&bar_a_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % a.stages, use = j / a.stages;
+        const int acc = j & 1, ause = j >> 1;
+        tc::mbar_wait(&bar_t_empty[acc], (ause & 1) ^ 1);
+        tc::mbar_wait(&bar_b_full[s], use & 1);
+        tc::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kTcBN;
+        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
+        const uint32_t bl = bh + a.nkb * kKBlockBytesB;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          const int steps = min(4, a.ksteps - kb * 4);
+          const uint32_t ah_kb = tc::smem_u32(a_hi + (size_t)kb * kKBlockBytesA);
+          const uint32_t al_kb = tc::smem_u32(a_lo + (size_t)kb * kKBlockBytesA);
+          for (int ks = 0; ks < steps; ++ks) {
+            const uint32_t off = ks * 32;  // 16 bf16 inside the 128-byte swizzle atom
+            const uint64_t dah = tc::umma_desc_sw128(ah_kb + off, 16, 1024);
+            const uint64_t dal = tc::umma_desc_sw128(al_kb + off, 16, 1024);
+            const uint64_t dbh = tc::umma_desc_sw128(bh + kb * kKBlockBytesB + off, 16, 1024);
+            const uint64_t dbl = tc::umma_desc_sw128(bl + kb * kKBlockBytesB + off, 16, 1024);
+            tc::umma_bf16(d_tmem, dah, dbh, idesc, accumulate);
+            tc::umma_bf16(d_tmem, dal, dbh, idesc, 1);
+            tc::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+            accumulate = 1;
+          }
+        }
+        tc::umma_commit(&bar_b_empty[s]);    // the ring slot can be refilled
+        tc::umma_commit(&bar_t_full[acc]);   // the accumulator is complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue
+    const int et = tid - 64;                  // 0..255
+    const int sp = warp & 3;                  // TMEM sub-partition of this warp
+    const int half = (warp - 2) >> 2;         // which 64-column half of the tile
+    const int row = sp * 32 + lane;
+    const bool row_ok = row < rows;
+    const int code_i = row_ok ? a.rcode[row0 + row] : 0;
+    const int seg_i = row_ok ? a.rseg[row0 + row] : -1;
+    float same = 0.f, diff = 0.f, self = 0.f;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int acc = j & 1, ause = j >> 1;
+      const int c0 = c_begin + j * kTcBN;
+      if (et < kTcBN) s_ccode[acc][et] = c0 + et < c_end ? a.ccode[c0 + et] : 0;
+      tc::named_bar_sync(1, kTcEpiThreads);
+      tc::mbar_wait(&bar_t_full[acc], ause & 1);
+      tc::tcgen05_fence_after();
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int cb = half * 64 + chunk * 32;
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + acc * kTcBN + cb + (static_cast<uint32_t>(sp * 32) << 16), v);
+        tc::tmem_ld_wait();
+        if (chunk == 1) {  // both loads of this warp are done: hand the accumulator back
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int c = c0 + cb + q;
+          const int cc = s_ccode[acc][cb + q];
+          float s = tc::fast_exp2(__uint_as_float(v[q]) * a.kappa_log2e);
+          s = c < c_end ? s : 0.f;
+          const bool match = a.mode == SPML_MODE_TAGS ? (code_i & cc) != 0 : code_i == cc;
+          same += match ? s : 0.f;
+          diff += match ? 0.f : s;
+          self += c == seg_i ? s : 0.f;
+        }
+      }
+    }
+    // the two column halves of a row live in different warps: combine in a fixed order
+    if (half == 1) {
+      s_part[row][0] = same;
+      s_part[row][1] = diff;
+      s_part[row][2] = self;
+    }
+    tc::named_bar_sync(1, kTcEpiThreads);
+    if (half == 0) {
+      same += s_part[row][0];
+      diff += s_part[row][1];
+      self += s_part[row][2];
+      float nll = 0.f;
+      if (row_ok) {
+        const float others = same - self;   // loss.py:64-70
+        const bool pos = others > 0.f;
+        const float num = pos ? others : self;
+        const float den = diff + num;
+        nll = -logf(num / den);
+        float* st = a.stats + (row0 + row) * 3;
+        st[0] = num;
+        st[1] = den;
+        st[2] = pos ? 1.f : 0.f;
+        if (a.nll) a.nll[row0 + row] = nll;
+      }
+      s_nll[row] = nll;
+    }
+    tc::named_bar_sync(1, kTcEpiThreads);
+    if (warp == 2) {
+      float v = s_nll[lane] + s_nll[lane + 32] + s_nll[lane + 64] + s_nll[lane + 96];
+      v = warp_sum(v);
+      if (lane == 0) *my_partial = v;
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, 2 * kTcBN);
+  }
+}
+
+// ------------------------------------------------------------------------- host side
+
+static int tc_tiles_x(const spml_segsort_desc& d) {
+  return (int)std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kTcBM));
+}
+
+bool segsort_tc_supported(const spml_segsort_desc& d) {
+  if (d.dim > 192 || d.dim < 1) return false;
+  if (d.n_rows <= 0 || d.m <= 0) return false;
+  if (d.proto_valid && (d.col_off || d.num_groups > 1)) return false;
+  if (d.n_rows >= (1ll << 31) - kTcBM || d.m >= (1ll << 31) - kTcBN) return false;
+  return true;
+}
+
+TcPlan segsort_tc_plan(const spml_segsort_desc& d, void* base) {
+  TcPlan p{};
+  p.dp = (d.dim + 7) & ~7;
+  p.nkb = (d.dim + 63) / 64;
+  p.ksteps = (d.dim + 15) / 16;
+  p.stages = p.nkb <= 2 ? 2 : 1;
+  char* ptr = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = ptr + off;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  p.partial = reinterpret_cast<float*>(take((size_t)d.num_groups * tc_tiles_x(d) * sizeof(float)));
+  p.eh = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.n_rows * p.dp * 2));
+  p.el = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.n_rows * p.dp * 2));
+  p.ph = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.m * p.dp * 2));
+  p.pl = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.m * p.dp * 2));
+  p.rcode = reinterpret_cast<int32_t*>(take((size_t)d.n_rows * 4));
+  p.rseg = reinterpret_cast<int32_t*>(take((size_t)d.n_rows * 4));
+  p.ccode = reinterpret_cast<int32_t*>(take((size_t)d.m * 4));
+  p.col_dst = reinterpret_cast<int32_t*>(take((size_t)d.m * 4));
+  p.col_src = reinterpret_cast<int32_t*>(take((size_t)d.m * 4));
+  p.col_count = reinterpret_cast<int32_t*>(take(16));
+  p.bytes = off;
+  return p;
+}
+
+// pre-pass shared by forward and backward: compact columns, split both operands
+int segsort_tc_prepare(const spml_segsort_desc& d, const TcPlan& p, cudaStream_t st) {
+  const bool compact = d.proto_valid != nullptr;
+  if (compact) {
+    compact_cols_kernel<<<1, 1024, 0, st>>>(d.proto_valid, (int)d.m, p.col_dst, p.col_src,
+                                            p.col_count);
+    SPML_LAUNCH_CHECK("compact_cols_kernel");
+  }
+  split_rows_kernel<<<(unsigned)ceil_div(d.n_rows, 8), 256, 0, st>>>(
+      d.emb, d.ld_emb, d.dim, p.dp, d.row_index, d.group_off, d.num_groups, d.n_rows, d.pix_code,
+      d.seg, compact ? p.col_dst : nullptr, d.m, p.eh, p.el, p.rcode, p.rseg);
+  SPML_LAUNCH_CHECK("split_rows_kernel");
+  split_protos_kernel<<<(unsigned)ceil_div(d.m, 8), 256, 0, st>>>(
+      d.protos, d.ld_protos, d.dim, p.dp, compact ? p.col_src : nullptr,
+      compact ? p.col_count : nullptr, d.m, d.proto_code, p.ph, p.pl, p.ccode);
+  SPML_LAUNCH_CHECK("split_protos_kernel");
+  return SPML_OK;
+}
+
+int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, float* nll,
+                   cudaStream_t st) {
+  int rc = segsort_tc_prepare(d, p, st);
+  if (rc != SPML_OK) return rc;
+  CUtensorMap map_eh, map_el, map_ph, map_pl;
+  const uint64_t pitch = (uint64_t)p.dp * 2;
+  if ((rc = make_tensor_map_bf16_2d(&map_eh, p.eh, p.dp, d.n_rows, pitch, 64, kTcBM))) return rc;
+  if ((rc = make_tensor_map_bf16_2d(&map_el, p.el, p.dp, d.n_rows, pitch, 64, kTcBM))) return rc;
+  if ((rc = make_tensor_map_bf16_2d(&map_ph, p.ph, p.dp, d.m, pitch, 64, kTcBN))) return rc;
+  if ((rc = make_tensor_map_bf16_2d(&map_pl, p.pl, p.dp, d.m, pitch, 64, kTcBN))) return rc;
+
+  TcFwdArgs a{};
+  a.group_off = d.group_off;
+  a.col_off = d.col_off;
+  a.col_count = d.proto_valid ? p.col_count : nullptr;
+  a.n_rows = d.n_rows;
+  a.m = d.m;
+  a.rcode = p.rcode;
+  a.rseg = p.rseg;
+  a.ccode = p.ccode;
+  a.stats = stats;
+  a.nll = nll;
+  a.partial = p.partial;
+  a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
+  a.mode = d.mode;
+  a.nkb = p.nkb;
+  a.ksteps = p.ksteps;
+  a.stages = p.stages;
+  const size_t smem = 1024 + (size_t)2 * p.nkb * kKBlockBytesA +
+                      (size_t)p.stages * 2 * p.nkb * kKBlockBytesB;
+  if (smem > 227 * 1024) {
+    set_error("segsort_fwd(tc): needs %zu bytes of shared memory", smem);
+    return SPML_E_UNSUPPORTED;
+  }
+  SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups);
+  segsort_fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+  SPML_LAUNCH_CHECK("segsort_fwd_tc_kernel");
+  return SPML_OK;
+}
+
+}  // namespace spml

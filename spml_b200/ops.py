@@ -257,7 +257,7 @@ class SegsortProblem:
 
   def __init__(self, pix_code, seg, proto_code, kappa, mode, reduction=_lib.REDUCE_MEAN,
                row_index=None, group_off=None, col_off=None, num_groups=1, n_rows=None,
-               max_rows_per_group=None, proto_valid=None):
+               max_rows_per_group=None, proto_valid=None, path='auto'):
     self.pix_code = _i64c(pix_code, 'segsort(pixel labels)').view(-1)
     self.seg = _i64c(seg, 'segsort(instance labels)').view(-1)
     self.proto_code = _i64c(proto_code, 'segsort(prototype labels)').view(-1)
@@ -268,6 +268,8 @@ class SegsortProblem:
     self.max_rows_per_group = (int(max_rows_per_group) if max_rows_per_group is not None
                                else self.n_rows)
     self.proto_valid = proto_valid
+    # 'fp32' / 'tc' pin the CUDA-core / tcgen05 kernels (tests compare the two)
+    self.path_bits = {'auto': 0, 'fp32': 1, 'tc': 2}[path]
     if proto_valid is not None and proto_valid.dtype != torch.uint8:
       self.proto_valid = proto_valid.to(torch.uint8)
 
@@ -280,7 +282,7 @@ class SegsortProblem:
     d.pix_code, d.seg = ptr(self.pix_code), ptr(self.seg)
     d.protos, d.ld_protos, d.m = ptr(protos), protos.stride(0), protos.shape[0]
     d.proto_code, d.proto_valid = ptr(self.proto_code), ptr(self.proto_valid)
-    d.kappa, d.mode, d.reduction, d.reserved = self.kappa, self.mode, self.reduction, 0
+    d.kappa, d.mode, d.reduction, d.reserved = self.kappa, self.mode, self.reduction, self.path_bits
     return d
 
 
