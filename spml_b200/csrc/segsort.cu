@@ -34,19 +34,6 @@ __device__ __forceinline__ void group_range(const spml_segsort_desc& d, int g, T
   t.c_end = d.col_off ? d.col_off[g + 1] : (int)d.m;
 }
 
-// 1 / (what the row's nll is divided by); see SPML_REDUCE_*.
-__device__ float reduction_weight(const spml_segsort_desc& d, int g) {
-  if (d.reduction == SPML_REDUCE_SUM) return 1.f;
-  if (d.reduction == SPML_REDUCE_MEAN || !d.group_off) {
-    const int64_t total =
-        d.group_off ? (int64_t)d.group_off[d.num_groups] - d.group_off[0] : d.n_rows;
-    return 1.f / (float)total;
-  }
-  int nonempty = 0;
-  for (int q = 0; q < d.num_groups; ++q) nonempty += d.group_off[q + 1] > d.group_off[q];
-  return 1.f / ((float)(d.group_off[g + 1] - d.group_off[g]) * (float)nonempty);
-}
-
 __device__ __forceinline__ bool codes_match(int mode, int64_t a, int64_t b) {
   return mode == SPML_MODE_TAGS ? (a & b) != 0 : a == b;
 }
@@ -532,7 +519,11 @@ size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
   const size_t fwd = (size_t)d->num_groups * spml::tiles_x_of(*d) * sizeof(float);
   const size_t bwd = (size_t)spml::proto_chunks_of(*d) * d->m * d->dim * sizeof(float);
   size_t need = 16 + (fwd > bwd ? fwd : bwd);
-  if (spml::segsort_tc_supported(*d)) need = std::max(need, spml::segsort_tc_plan(*d, nullptr).bytes);
+  if (spml::segsort_tc_supported(*d)) {
+    const size_t tc = spml::segsort_tc_plan(*d, nullptr).bytes +
+                      (size_t)spml::segsort_tc_proto_chunks(*d) * d->m * d->dim * sizeof(float);
+    need = std::max(need, tc);
+  }
   return need;
 }
 
@@ -587,6 +578,31 @@ int spml_segsort_bwd(const spml_segsort_desc* d, const float* stats, const float
   if (dprotos && d->m > 0)
     SPML_CUDA(cudaMemsetAsync(dprotos, 0, (size_t)d->m * d->dim * sizeof(float), st));
   if (d->n_rows == 0 || d->m == 0 || d->max_rows_per_group == 0) return SPML_OK;
+
+  if (use_tc_path(*d)) {
+    if (!workspace || workspace_bytes < spml_segsort_workspace_bytes(d)) {
+      set_error("segsort_bwd: workspace %zu < %zu bytes", workspace_bytes,
+                spml_segsort_workspace_bytes(d));
+      return SPML_E_WORKSPACE;
+    }
+    const TcPlan plan = segsort_tc_plan(*d, workspace);
+    const int chunks = segsort_tc_proto_chunks(*d);
+    float* partial = nullptr;
+    const size_t partial_bytes = (size_t)chunks * d->m * d->dim * sizeof(float);
+    if (dprotos) {
+      partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + plan.bytes);
+      SPML_CUDA(cudaMemsetAsync(partial, 0, partial_bytes, st));
+    }
+    rc = segsort_bwd_tc(*d, plan, stats, grad_loss, beta, demb, ld_demb, partial, chunks, st);
+    if (rc != SPML_OK) return rc;
+    if (dprotos) {
+      const int64_t count = d->m * d->dim;
+      reduce_chunks_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, chunks, count,
+                                                                           dprotos);
+      SPML_LAUNCH_CHECK("reduce_chunks_kernel");
+    }
+    return SPML_OK;
+  }
 
   if (demb) {
     const size_t smem = ((size_t)dpad * (LDA + LDB) + (size_t)BN * ldp + (size_t)BN * LDA) * sizeof(float);

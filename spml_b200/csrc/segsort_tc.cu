@@ -104,6 +104,8 @@ __global__ void compact_cols_kernel(const uint8_t* __restrict__ valid, int m,
   if (threadIdx.x == 0) *count = s_base;
 }
 
+constexpr int kPadRows = 128;   // rows past the live count that are kept finite (zero)
+
 __device__ __forceinline__ void split_store(float x, float y, __nv_bfloat16* hi,
                                             __nv_bfloat16* lo, int64_t at) {
   const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
@@ -126,7 +128,14 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int64_t ld, int d
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t live = group_off ? (int64_t)group_off[num_groups] : n_rows;
-  if (r >= live || r >= n_rows) return;
+  if (r >= n_rows) return;
+  if (r >= live) {
+    // tiles that straddle the live count feed these rows to the K dimension of the second
+    // GEMM, where even a zero weight cannot cancel a NaN: keep one tile of zeros
+    if (r < live + kPadRows)
+      for (int q = lane * 2; q < dp; q += 64) split_store(0.f, 0.f, hi, lo, r * dp + q);
+    return;
+  }
   const int64_t orig = row_index ? (int64_t)row_index[r] : r;
   const float* xr = x + orig * ld;
   for (int q = lane * 2; q < dp; q += 64) {
@@ -152,7 +161,12 @@ __global__ void split_protos_kernel(const float* __restrict__ p, int64_t ld, int
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t live = col_count ? (int64_t)*col_count : m;
-  if (k >= live || k >= m) return;
+  if (k >= m) return;
+  if (k >= live) {
+    if (k < live + kPadRows)
+      for (int q = lane * 2; q < dp; q += 64) split_store(0.f, 0.f, hi, lo, k * dp + q);
+    return;
+  }
   const int64_t orig = col_src ? (int64_t)col_src[k] : k;
   const float* pr = p + orig * ld;
   for (int q = lane * 2; q < dp; q += 64) {
@@ -388,6 +402,370 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   }
 }
 
+// ------------------------------------------------------------------------- backward kernel
+//
+// One kernel, two roles.  The OWNER side is a resident tile of 128 entities whose
+// gradient accumulates in TMEM; the STREAMED side passes by in tiles of 64:
+//   kProtoOwner = false : owner = 128 pixel rows, streamed = prototypes, output dE
+//   kProtoOwner = true  : owner = 128 prototypes, streamed = pixel rows, output dP
+// Per streamed tile:   GEMM 1  S^(T) = owner . streamed^T          (K = D, both K-major)
+//                      epilogue G = coef S ((diff + numset) / den - numset / num)
+//                               -> bf16 hi / lo, written as a K-major SW128 operand
+//                      GEMM 2  d(owner) += G . streamed            (K = 64; the streamed
+//                               tile is re-used as an MN-major operand: same bytes, the
+//                               128-byte rows now index K)
+// The similarity is recomputed instead of stored, as in the fp32 path.
+
+constexpr int kBwdBM = 128;
+constexpr int kBwdBN = 64;
+constexpr int kBwdTileBytesA = kBwdBM * 128;   // one 64-wide K block of the owner tile
+constexpr int kBwdTileBytesB = kBwdBN * 128;   // one 64-wide block of the streamed tile
+constexpr int kBwdGBytes = kBwdBM * 128;       // G tile, 128 x 64 bf16
+
+struct TcBwdArgs {
+  spml_segsort_desc d;        // for group ranges / reduction weights
+  const int32_t* col_count;   // compact column count (proto_valid) or nullptr
+  const int32_t* col_src;     // compact column -> original column, or nullptr
+  const int32_t* rcode;
+  const int32_t* rseg;
+  const int32_t* ccode;
+  const float* stats;
+  const float* grad_loss;
+  float* out;                 // demb, or the [chunks][m][dim] prototype partials
+  int64_t ld_out;
+  float beta;
+  float kappa_log2e;
+  int nkb, ksteps, stages;
+  int n2;                     // GEMM 2 N: dim rounded up to 16
+  int tmem_cols;
+};
+
+struct PixMeta {              // per-pixel constants of the gradient
+  float inv_num, inv_den, pos, coef;
+};
+
+__device__ __forceinline__ float grad_elem(float z, float kl2e, int mode, int code_pix,
+                                           int code_pro, bool own, const PixMeta& pm, bool valid) {
+  const float s = tc::fast_exp2(z * kl2e);
+  const bool match = mode == SPML_MODE_TAGS ? (code_pix & code_pro) != 0 : code_pix == code_pro;
+  const float same = match ? 1.f : 0.f, self = own ? 1.f : 0.f;
+  const float numset = pm.pos != 0.f ? same - self : self;
+  const float g = pm.coef * s * ((1.f - same + numset) * pm.inv_den - numset * pm.inv_num);
+  return valid ? g : 0.f;
+}
+
+__device__ __forceinline__ PixMeta load_pix_meta(const TcBwdArgs& a, int64_t r, float weight) {
+  const float* st = a.stats + r * 3;
+  PixMeta pm;
+  pm.inv_num = 1.f / st[0];
+  pm.inv_den = 1.f / st[1];
+  pm.pos = st[2];
+  pm.coef = a.d.kappa * (*a.grad_loss) * weight;
+  return pm;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float x, float y) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <bool kProtoOwner>
+__global__ void __launch_bounds__(kTcThreads, 1)
+segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
+                      const __grid_constant__ CUtensorMap map_al,
+                      const __grid_constant__ CUtensorMap map_bh,
+                      const __grid_constant__ CUtensorMap map_bl, const TcBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
+      bar_t_empty[2], bar_g_full[2], bar_g_empty[2], bar_d_full;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int32_t s_code[2][kBwdBN];
+  __shared__ int32_t s_seg[2][kBwdBN];
+  __shared__ PixMeta s_pm[2][kBwdBN];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.y;
+  const spml_segsort_desc& d = a.d;
+  const int64_t r_begin = d.group_off ? d.group_off[g] : 0;
+  const int64_t r_end = d.group_off ? d.group_off[g + 1] : d.n_rows;
+  const int c_begin = d.col_off ? d.col_off[g] : 0;
+  const int c_end = a.col_count ? *a.col_count : (d.col_off ? d.col_off[g + 1] : (int)d.m);
+
+  // owner tile [o0, o0 + 128) and streamed range [s_lo, s_hi) in steps of 64
+  int64_t o0, o_end, s_lo, s_hi;
+  if (!kProtoOwner) {
+    o0 = r_begin + (int64_t)blockIdx.x * kBwdBM;
+    o_end = r_end;
+    s_lo = c_begin;
+    s_hi = c_end;
+  } else {
+    o0 = c_begin + (int64_t)blockIdx.x * kBwdBM;
+    o_end = c_end;
+    const int64_t steps = (r_end - r_begin + kBwdBN - 1) / kBwdBN;
+    const int64_t per = (steps + gridDim.z - 1) / gridDim.z;
+    s_lo = r_begin + (int64_t)blockIdx.z * per * kBwdBN;
+    s_hi = min(r_end, s_lo + per * kBwdBN);
+  }
+  if (o0 >= o_end) return;
+  const int owned = (int)min((int64_t)kBwdBM, o_end - o0);
+  if (s_lo >= s_hi) {
+    // nothing streams past this tile: dP partials are pre-zeroed, dE rows are written here
+    if (!kProtoOwner && warp >= 2 && (warp - 2) < 4) {
+      const int row = (warp - 2) * 32 + lane;
+      if (row < owned) {
+        const int64_t orow = o0 + row;
+        float* out_row = a.out + (d.row_index ? (int64_t)d.row_index[orow] : orow) * a.ld_out;
+        for (int col = 0; col < d.dim; ++col)
+          out_row[col] = a.beta != 0.f ? a.beta * out_row[col] : 0.f;
+      }
+    }
+    return;
+  }
+  const int ntiles = (int)((s_hi - s_lo + kBwdBN - 1) / kBwdBN);
+  const float weight = reduction_weight(d, g);
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + (size_t)a.nkb * kBwdTileBytesA;
+  uint8_t* b_ring = a_lo + (size_t)a.nkb * kBwdTileBytesA;
+  const uint32_t stage_bytes = 2u * a.nkb * kBwdTileBytesB;
+  uint8_t* g_ring = b_ring + (size_t)a.stages * stage_bytes;   // [2][hi | lo][16 KB]
+
+  if (warp == 0 && lane == 0) {
+    tc::mbar_init(&bar_a_full, 1);
+    tc::mbar_init(&bar_d_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_b_full[s], 1);
+      tc::mbar_init(&bar_b_empty[s], 1);
+      tc::mbar_init(&bar_t_full[s], 1);
+      tc::mbar_init(&bar_t_empty[s], kTcEpiThreads / 32);
+      tc::mbar_init(&bar_g_full[s], kTcEpiThreads);
+      tc::mbar_init(&bar_g_empty[s], 1);
+    }
+    tc::fence_barrier_init();
+    tc::prefetch_tensormap(&map_ah);
+    tc::prefetch_tensormap(&map_al);
+    tc::prefetch_tensormap(&map_bh);
+    tc::prefetch_tensormap(&map_bl);
+  }
+  if (warp == 1) tc::tmem_alloc(&s_tmem_base, a.tmem_cols);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t tmem_acc = tmem_base + 2 * kBwdBN;   // d(owner) accumulator columns
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      tc::mbar_expect_tx(&bar_a_full, 2u * a.nkb * kBwdTileBytesA);
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        tc::tma_load_2d(&map_ah, &bar_a_full, a_hi + (size_t)kb * kBwdTileBytesA, kb * 64,
+                        (int32_t)o0);
+        tc::tma_load_2d(&map_al, &bar_a_full, a_lo + (size_t)kb * kBwdTileBytesA, kb * 64,
+                        (int32_t)o0);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % a.stages, use = j / a.stages;
+        tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);
+        tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
+        uint8_t* bh = b_ring + (size_t)s * stage_bytes;
+        uint8_t* bl = bh + (size_t)a.nkb * kBwdTileBytesB;
+        const int32_t s0 = (int32_t)(s_lo + (int64_t)j * kBwdBN);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          tc::tma_load_2d(&map_bh, &bar_b_full[s], bh + (size_t)kb * kBwdTileBytesB, kb * 64, s0);
+          tc::tma_load_2d(&map_bl, &bar_b_full[s], bl + (size_t)kb * kBwdTileBytesB, kb * 64, s0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = tc::umma_idesc_bf16(kBwdBM, kBwdBN, 0, 0);
+      const uint32_t idesc2 = tc::umma_idesc_bf16(kBwdBM, a.n2, 0, 1);
+      auto gemm1 = [&](int j) {
+        const int s = j % a.stages, use = j / a.stages;
+        const int acc = j & 1, ause = j >> 1;
+        tc::mbar_wait(&bar_t_empty[acc], (ause & 1) ^ 1);
+        tc::mbar_wait(&bar_b_full[s], use & 1);
+        tc::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBwdBN;
+        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
+        const uint32_t bl = bh + a.nkb * kBwdTileBytesB;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          const int steps = min(4, a.ksteps - kb * 4);
+          const uint32_t ah_kb = tc::smem_u32(a_hi + (size_t)kb * kBwdTileBytesA);
+          const uint32_t al_kb = tc::smem_u32(a_lo + (size_t)kb * kBwdTileBytesA);
+          for (int ks = 0; ks < steps; ++ks) {
+            const uint32_t off = ks * 32;
+            const uint64_t dah = tc::umma_desc_sw128(ah_kb + off, 16, 1024);
+            const uint64_t dal = tc::umma_desc_sw128(al_kb + off, 16, 1024);
+            const uint64_t dbh = tc::umma_desc_sw128(bh + kb * kBwdTileBytesB + off, 16, 1024);
+            const uint64_t dbl = tc::umma_desc_sw128(bl + kb * kBwdTileBytesB + off, 16, 1024);
+            tc::umma_bf16(d_tmem, dah, dbh, idesc1, accumulate);
+            tc::umma_bf16(d_tmem, dal, dbh, idesc1, 1);
+            tc::umma_bf16(d_tmem, dah, dbl, idesc1, 1);
+            accumulate = 1;
+          }
+        }
+        tc::umma_commit(&bar_t_full[acc]);
+      };
+      tc::mbar_wait(&bar_a_full, 0);
+      gemm1(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (a.stages == 2 && j + 1 < ntiles) gemm1(j + 1);
+        const int s = j % a.stages, gb = j & 1, guse = j >> 1;
+        tc::mbar_wait(&bar_g_full[gb], guse & 1);
+        tc::tcgen05_fence_after();
+        const uint32_t gh = tc::smem_u32(g_ring + (size_t)gb * 2 * kBwdGBytes);
+        const uint32_t gl = gh + kBwdGBytes;
+        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
+        const uint32_t bl = bh + a.nkb * kBwdTileBytesB;
+        for (int ks = 0; ks < kBwdBN / 16; ++ks) {
+          // A: G tile, K-major, 16 columns = 32 bytes inside the swizzle atom
+          const uint64_t dgh = tc::umma_desc_sw128(gh + ks * 32, 16, 1024);
+          const uint64_t dgl = tc::umma_desc_sw128(gl + ks * 32, 16, 1024);
+          // B: streamed tile, MN-major: 16 K rows = 2048 bytes; next 64-wide N atom = next
+          // K block of the stage (LBO)
+          const uint64_t dbh = tc::umma_desc_sw128(bh + ks * 2048, kBwdTileBytesB, 1024);
+          const uint64_t dbl = tc::umma_desc_sw128(bl + ks * 2048, kBwdTileBytesB, 1024);
+          const uint32_t accumulate = (j > 0 || ks > 0) ? 1u : 0u;
+          tc::umma_bf16(tmem_acc, dgh, dbh, idesc2, accumulate);
+          tc::umma_bf16(tmem_acc, dgl, dbh, idesc2, 1);
+          tc::umma_bf16(tmem_acc, dgh, dbl, idesc2, 1);
+        }
+        tc::umma_commit(&bar_b_empty[s]);
+        tc::umma_commit(&bar_g_empty[gb]);
+        if (a.stages == 1 && j + 1 < ntiles) gemm1(j + 1);
+      }
+      tc::umma_commit(&bar_d_full);
+    }
+  } else {
+    // ===================================================================== epilogue
+    const int et = tid - 64;
+    const int sp = warp & 3;
+    const int half = (warp - 2) >> 2;          // 32-column half of the 64-wide S tile
+    const int row = sp * 32 + lane;            // owner entity of this thread
+    const bool row_ok = row < owned;
+    const int64_t orow = o0 + row;
+    // owner-side constants
+    int code_o = 0, seg_o = -1;
+    PixMeta pm_o = {0.f, 0.f, 0.f, 0.f};
+    if (row_ok) {
+      if (!kProtoOwner) {
+        code_o = a.rcode[orow];
+        seg_o = a.rseg[orow];
+        pm_o = load_pix_meta(a, orow, weight);
+      } else {
+        code_o = a.ccode[orow];
+      }
+    }
+    const uint32_t sw = (row & 7);
+    const uint32_t g_row_off = (row >> 3) * 1024 + sw * 128;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int acc = j & 1, ause = j >> 1, gb = j & 1, guse = j >> 1;
+      const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
+      if (et < kBwdBN) {
+        const int64_t e = s0 + et;
+        const bool in = e < s_hi;
+        if (!kProtoOwner) {
+          s_code[acc][et] = in ? a.ccode[e] : 0;
+        } else {
+          s_code[acc][et] = in ? a.rcode[e] : 0;
+          s_seg[acc][et] = in ? a.rseg[e] : -1;
+          PixMeta z = {0.f, 0.f, 0.f, 0.f};
+          s_pm[acc][et] = in ? load_pix_meta(a, e, weight) : z;
+        }
+      }
+      tc::named_bar_sync(1, kTcEpiThreads);
+      tc::mbar_wait(&bar_t_full[acc], ause & 1);
+      tc::tcgen05_fence_after();
+      uint32_t v[32];
+      const int cb = half * 32;
+      tc::tmem_ld_32x32(tmem_base + acc * kBwdBN + cb + (static_cast<uint32_t>(sp * 32) << 16), v);
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
+
+      float gv[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int k = cb + q;
+        const bool valid = row_ok && (s0 + k < s_hi);
+        const float z = __uint_as_float(v[q]);
+        if (!kProtoOwner) {
+          gv[q] = grad_elem(z, a.kappa_log2e, d.mode, code_o, s_code[acc][k],
+                            seg_o == (int)(s0 + k), pm_o, valid);
+        } else {
+          gv[q] = grad_elem(z, a.kappa_log2e, d.mode, s_code[acc][k], code_o,
+                            s_seg[acc][k] == (int)orow, s_pm[acc][k], valid);
+        }
+      }
+      tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
+      uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
+      uint8_t* gl = gh + kBwdGBytes;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+          const float x = gv[c4 * 8 + p2 * 2], y = gv[c4 * 8 + p2 * 2 + 1];
+          const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+          hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
+          lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
+        }
+        const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4);
+        const uint32_t off = g_row_off + ((chunk ^ sw) << 4);
+        *reinterpret_cast<uint4*>(gh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(gl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bar_g_full[gb]);
+    }
+
+    // ---- d(owner) out of TMEM
+    tc::mbar_wait(&bar_d_full, 0);
+    tc::tcgen05_fence_after();
+    float* out_row = nullptr;
+    if (row_ok) {
+      if (!kProtoOwner) {
+        const int64_t orig = d.row_index ? (int64_t)d.row_index[orow] : orow;
+        out_row = a.out + orig * a.ld_out;
+      } else {
+        const int64_t orig = a.col_src ? (int64_t)a.col_src[orow] : orow;
+        out_row = a.out + ((size_t)blockIdx.z * d.m + orig) * d.dim;
+      }
+    }
+    const int nchunks = (a.n2 + 31) / 32;
+    for (int ch = half; ch < nchunks; ch += 2) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_acc + ch * 32 + (static_cast<uint32_t>(sp * 32) << 16), v);
+      tc::tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int col = ch * 32 + q;
+          if (col < d.dim) {
+            const float val = __uint_as_float(v[q]);
+            out_row[col] = (!kProtoOwner && a.beta != 0.f) ? a.beta * out_row[col] + val : val;
+          }
+        }
+      }
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------- host side
 
 static int tc_tiles_x(const spml_segsort_desc& d) {
@@ -488,6 +866,73 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
   dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups);
   segsort_fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
   SPML_LAUNCH_CHECK("segsort_fwd_tc_kernel");
+  return SPML_OK;
+}
+
+
+int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
+  const int64_t col_tiles = std::max<int64_t>(1, ceil_div(d.m, kBwdBM));
+  const int64_t steps = std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kBwdBN));
+  int64_t chunks = ceil_div(2 * 148, col_tiles * d.num_groups);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(chunks, steps));
+}
+
+int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
+                   const float* grad_loss, float beta, float* demb, int64_t ld_demb,
+                   float* proto_partial, int chunks, cudaStream_t st) {
+  int rc = segsort_tc_prepare(d, p, st);
+  if (rc != SPML_OK) return rc;
+  const uint64_t pitch = (uint64_t)p.dp * 2;
+  TcBwdArgs a{};
+  a.d = d;
+  a.col_count = d.proto_valid ? p.col_count : nullptr;
+  a.col_src = d.proto_valid ? p.col_src : nullptr;
+  a.rcode = p.rcode;
+  a.rseg = p.rseg;
+  a.ccode = p.ccode;
+  a.stats = stats;
+  a.grad_loss = grad_loss;
+  a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
+  a.nkb = p.nkb;
+  a.ksteps = p.ksteps;
+  a.stages = p.nkb <= 2 ? 2 : 1;
+  a.n2 = (d.dim + 15) & ~15;
+  a.tmem_cols = (2 * kBwdBN + a.n2) <= 256 ? 256 : 512;
+  const size_t smem = 1024 + (size_t)2 * p.nkb * kBwdTileBytesA +
+                      (size_t)a.stages * 2 * p.nkb * kBwdTileBytesB + (size_t)4 * kBwdGBytes;
+  if (smem > 227 * 1024) {
+    set_error("segsort_bwd(tc): needs %zu bytes of shared memory", smem);
+    return SPML_E_UNSUPPORTED;
+  }
+  CUtensorMap e128h, e128l, e64h, e64l, p128h, p128l, p64h, p64l;
+  if (demb) {
+    if ((rc = make_tensor_map_bf16_2d(&e128h, p.eh, p.dp, d.n_rows, pitch, 64, kBwdBM))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&e128l, p.el, p.dp, d.n_rows, pitch, 64, kBwdBM))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&p64h, p.ph, p.dp, d.m, pitch, 64, kBwdBN))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&p64l, p.pl, p.dp, d.m, pitch, 64, kBwdBN))) return rc;
+    a.out = demb;
+    a.ld_out = ld_demb;
+    a.beta = beta;
+    SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups, 1);
+    segsort_bwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(e128h, e128l, p64h, p64l, a);
+    SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<emb>");
+  }
+  if (proto_partial) {
+    if ((rc = make_tensor_map_bf16_2d(&p128h, p.ph, p.dp, d.m, pitch, 64, kBwdBM))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&p128l, p.pl, p.dp, d.m, pitch, 64, kBwdBM))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&e64h, p.eh, p.dp, d.n_rows, pitch, 64, kBwdBN))) return rc;
+    if ((rc = make_tensor_map_bf16_2d(&e64l, p.el, p.dp, d.n_rows, pitch, 64, kBwdBN))) return rc;
+    a.out = proto_partial;
+    a.ld_out = d.dim;
+    a.beta = 0.f;
+    SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(d.m, kBwdBM), (unsigned)d.num_groups, (unsigned)chunks);
+    segsort_bwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(p128h, p128l, e64h, e64l, a);
+    SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<proto>");
+  }
   return SPML_OK;
 }
 

@@ -20,10 +20,31 @@ struct TcPlan {
   size_t bytes;
 };
 
+#ifdef __CUDACC__
+// 1 / (what a row's nll is divided by); see SPML_REDUCE_* in the header.
+__device__ inline float reduction_weight(const spml_segsort_desc& d, int g) {
+  if (d.reduction == SPML_REDUCE_SUM) return 1.f;
+  if (d.reduction == SPML_REDUCE_MEAN || !d.group_off) {
+    const int64_t total =
+        d.group_off ? (int64_t)d.group_off[d.num_groups] - d.group_off[0] : d.n_rows;
+    return 1.f / (float)total;
+  }
+  int nonempty = 0;
+  for (int q = 0; q < d.num_groups; ++q) nonempty += d.group_off[q + 1] > d.group_off[q];
+  return 1.f / ((float)(d.group_off[g + 1] - d.group_off[g]) * (float)nonempty);
+}
+#endif
+
 bool segsort_tc_supported(const spml_segsort_desc& d);
 TcPlan segsort_tc_plan(const spml_segsort_desc& d, void* base);
 int segsort_tc_prepare(const spml_segsort_desc& d, const TcPlan& p, cudaStream_t st);
 int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, float* nll,
                    cudaStream_t st);
+// backward: demb (nullable) and dprotos (nullable); `proto_partial` is the zeroed
+// [chunks][m][dim] buffer the prototype-gradient CTAs write, reduced by the caller.
+int segsort_tc_proto_chunks(const spml_segsort_desc& d);
+int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
+                   const float* grad_loss, float beta, float* demb, int64_t ld_demb,
+                   float* proto_partial, int chunks, cudaStream_t st);
 
 }  // namespace spml
