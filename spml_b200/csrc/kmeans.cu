@@ -1,141 +1,246 @@
 // A4-A6: batched spherical k-means with initial labels
 // (reference spml/utils/segsort/common.py:11-97).
 //
-// One launch = E-step against the prototypes of the previous launch fused with the
-// accumulation of the next M-step, so every iteration reads the embeddings once:
-// T iterations take T + 1 launches.  Segment sums are 64-bit fixed point
-// (common.cuh) so the clustering is bit-reproducible whatever the tiling; the
-// consumer normalises the sums when it stages the prototype tile.
+// The whole clustering (T iterations, every image of the batch) is ONE persistent
+// cooperative launch: each CTA owns a fixed set of 128-pixel tiles, keeps its tile
+// resident in shared memory when it has only one, and the iterations are separated
+// by a grid-wide barrier instead of kernel boundaries.  An iteration is the
+// reference's M-step (segment sums, L2-normalise) + E-step (argmax of x . P^T); the
+// E-step of iteration t is fused with the accumulation of the M-step of t + 1, so
+// the pixels are touched once per iteration.
+//
+// Segment sums are 64-bit fixed point (common.cuh): integer atomics are associative,
+// so the clustering is bit-reproducible whatever the tiling or scheduling.  The
+// consumer turns the sums into unit prototypes when it stages them.
 #include <math.h>
+
+#include <algorithm>
 
 #include "tile_gemm.cuh"
 
 namespace spml {
 
-struct KmeansStep {
+struct KmeansArgs {
   const float* x;            // [rows, dim]
-  const int32_t* img_off;    // [batch + 1] or nullptr (single image of `rows_total` rows)
+  const int32_t* img_off;    // [batch + 1] or nullptr (one image of `rows_total` rows)
   int64_t rows_total;
+  int batch, tiles_per_img;
   int dim, dpad;
   int num_clusters;          // stride of the per-image prototype arrays
   const int32_t* k_per_image;
-  const long long* sums_in;  // [batch, K, dim] fixed point, or nullptr
-  const float* protos_in;    // [K, dim] ready prototypes (A5), or nullptr
-  long long* sums_out;       // [batch, K, dim] or nullptr
+  long long* sums;           // [iterations][batch][K][dim] fixed point, zeroed
+  const float* protos_in;    // A5: ready prototypes [K, dim] instead of sums
   int* poison;
-  const int32_t* labels_in;  // used when there is no E-step (first launch)
+  unsigned* barrier;         // grid barrier counter, zeroed
+  int iterations;
+  const int32_t* labels_in;  // initial labels
   int32_t* labels_out;       // nullable
   int64_t* labels_out64;     // nullable
   float eps;
 };
 
-__global__ void __launch_bounds__(kGemmThreads) kmeans_step_kernel(KmeansStep p) {
+struct Tile {
+  int b;
+  int64_t row0;
+  int rows;
+};
+
+__device__ __forceinline__ bool tile_of(const KmeansArgs& p, int t, Tile& tile) {
+  tile.b = t / p.tiles_per_img;
+  const int64_t first = p.img_off ? p.img_off[tile.b] : 0;
+  const int64_t last = p.img_off ? p.img_off[tile.b + 1] : p.rows_total;
+  tile.row0 = first + (int64_t)(t % p.tiles_per_img) * BM;
+  tile.rows = (int)min((int64_t)BM, last - tile.row0);
+  return tile.row0 < last;
+}
+
+// Bt[d][k] = unit prototype k0 + k of image b: from fixed-point sums (normalised here,
+// common.py:39) or from ready prototypes.  One warp per prototype, lanes across d; the
+// eight prototypes of a warp are fetched before the first reduction.
+__device__ __forceinline__ void stage_prototypes(const KmeansArgs& p, const long long* sums_b,
+                                                 int k0, int kc, float* Bt) {
+  constexpr int kWarps = kGemmThreads / 32;
+  constexpr int kCols = BN / kWarps;            // 8 prototypes per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[kCols][kMaxSlots];
+#pragma unroll
+  for (int i = 0; i < kCols; ++i) {
+    const int k = warp + i * kWarps;
+    const bool live = k < kc;
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) {
+      const int d = lane + 32 * s;
+      float x = 0.f;
+      if (live && d < p.dim)
+        x = sums_b ? from_fixed(sums_b[(int64_t)(k0 + k) * p.dim + d])
+                   : p.protos_in[(int64_t)(k0 + k) * p.dim + d];
+      v[i][s] = x;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kCols; ++i) {
+    const int k = warp + i * kWarps;
+    float div = 1.f;
+    if (sums_b) {
+      float ss = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxSlots; ++s) ss += v[i][s] * v[i][s];
+      const float nrm = sqrtf(warp_sum(ss));
+      div = nrm >= p.eps ? nrm : p.eps;
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) {
+      const int d = lane + 32 * s;
+      if (d < p.dpad) Bt[d * LDB + k] = sums_b ? v[i][s] / div : v[i][s];
+    }
+  }
+}
+
+// E-step for the tile in At: s_lab[r] = argmax_k x_r . p_k, first index on ties.
+__device__ __forceinline__ void assign_tile(const KmeansArgs& p, const long long* sums_b, int kb,
+                                            const float* At, float* Bt, int* s_lab) {
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  float best_v[TM];
+  int best_k[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) best_v[i] = -INFINITY, best_k[i] = 0;
+  for (int k0 = 0; k0 < kb; k0 += BN) {
+    const int kc = min(BN, kb - k0);
+    __syncthreads();  // the previous prototype tile is no longer read
+    stage_prototypes(p, sums_b, k0, kc, Bt);
+    __syncthreads();
+    float acc[TM][TN];
+    gemm_nt_tile(At, Bt, p.dpad, ty, tx, acc);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int k = k0 + tx * TN + j;
+      if (k < kb) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          if (acc[i][j] > best_v[i]) best_v[i] = acc[i][j], best_k[i] = k;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v[i], o);
+      const int ok = __shfl_xor_sync(0xffffffffu, best_k[i], o);
+      if (ov > best_v[i] || (ov == best_v[i] && ok < best_k[i])) best_v[i] = ov, best_k[i] = ok;
+    }
+    if (tx == 0) s_lab[ty * TM + i] = best_k[i];
+  }
+  __syncthreads();
+}
+
+constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
+
+// M-step accumulation for the tile: each warp walks 16 consecutive rows with its lanes
+// across the channels and flushes a fixed-point run total whenever the label changes
+// (neighbouring pixels mostly share a cluster, so there are few atomics).
+__device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile& tile,
+                                                const float* At, const int* s_lab,
+                                                long long* sums_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = BM / (kGemmThreads / 32);
+  const int r0 = warp * per, r1 = min(tile.rows, r0 + per);
+  long long run[kAccSlots];
+#pragma unroll
+  for (int s = 0; s < kAccSlots; ++s) run[s] = 0;
+  int run_lab = -1;
+  for (int r = r0; r < r1; ++r) {
+    const int lab = s_lab[r];
+    if (lab != run_lab) {
+      if (run_lab >= 0) {
+#pragma unroll
+        for (int s = 0; s < kAccSlots; ++s) {
+          const int d = lane + 32 * s;
+          if (d < p.dim && run[s] != 0)
+            atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d], run[s]);
+          run[s] = 0;
+        }
+      }
+      run_lab = lab;
+    }
+    // the tile is already in shared memory (transposed): no second trip to L2
+#pragma unroll
+    for (int s = 0; s < kAccSlots; ++s) {
+      const int d = lane + 32 * s;
+      if (d < p.dim) run[s] += to_fixed(At[d * LDA + r], p.poison);
+    }
+  }
+  if (run_lab >= 0) {
+#pragma unroll
+    for (int s = 0; s < kAccSlots; ++s) {
+      const int d = lane + 32 * s;
+      if (d < p.dim && run[s] != 0) atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d], run[s]);
+    }
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Launched cooperatively (every CTA resident), grid <= number of tiles.
+__global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansArgs p) {
   extern __shared__ __align__(16) float smem[];
   float* At = smem;                       // [dpad][LDA]
   float* Bt = At + (size_t)p.dpad * LDA;  // [dpad][LDB]
   __shared__ int s_lab[BM];
+  const int tid = threadIdx.x;
+  const int total_tiles = p.batch * p.tiles_per_img;
+  const bool resident = (int)gridDim.x >= total_tiles;   // one tile per CTA: load it once
+  const size_t per_iter = (size_t)p.batch * p.num_clusters * p.dim;
 
-  const int b = blockIdx.y;
-  const int64_t first = p.img_off ? p.img_off[b] : 0;
-  const int64_t last = p.img_off ? p.img_off[b + 1] : p.rows_total;
-  const int64_t row0 = first + (int64_t)blockIdx.x * BM;
-  if (row0 >= last) return;
-  const int rows = (int)min((int64_t)BM, last - row0);
-  const int kb = p.k_per_image ? p.k_per_image[b] : p.num_clusters;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid / 16, tx = tid % 16;
-
-  load_rows_transposed<BM, LDA>(At, p.x, p.dim, nullptr, row0, rows, p.dim, p.dpad);
-
-  if (p.sums_in || p.protos_in) {
-    float best_v[TM];
-    int best_k[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) best_v[i] = -INFINITY, best_k[i] = 0;
-    for (int k0 = 0; k0 < kb; k0 += BN) {
-      const int kc = min(BN, kb - k0);
-      __syncthreads();  // the previous prototype tile is no longer read
-      for (int k = warp; k < BN; k += kGemmThreads / 32) {
-        for (int d = lane; d < p.dpad; d += 32) {
-          float v = 0.f;
-          if (k < kc && d < p.dim) {
-            const int64_t at = ((int64_t)b * p.num_clusters + k0 + k) * p.dim + d;
-            v = p.sums_in ? from_fixed(p.sums_in[at]) : p.protos_in[(int64_t)(k0 + k) * p.dim + d];
-          }
-          Bt[d * LDB + k] = v;
-        }
-      }
-      __syncthreads();
-      if (p.sums_in) {  // prototype = sum / max(||sum||, eps)  (common.py:39)
-        if (tid < BN) {
-          float ss = 0.f;
-          for (int d = 0; d < p.dpad; ++d) {
-            const float v = Bt[d * LDB + tid];
-            ss += v * v;
-          }
-          const float nrm = sqrtf(ss);
-          const float div = nrm >= p.eps ? nrm : p.eps;
-          for (int d = 0; d < p.dpad; ++d) Bt[d * LDB + tid] /= div;
-        }
+  for (int it = 0; it <= p.iterations; ++it) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      Tile tile;
+      if (!tile_of(p, t, tile)) continue;
+      const int kb = p.k_per_image ? p.k_per_image[tile.b] : p.num_clusters;
+      const size_t img = (size_t)tile.b * p.num_clusters * p.dim;
+      if (!resident || it == 0) {
         __syncthreads();
+        load_rows_transposed<BM, LDA>(At, p.x, p.dim, nullptr, tile.row0, tile.rows, p.dim,
+                                      p.dpad);
       }
-      float acc[TM][TN];
-      gemm_nt_tile(At, Bt, p.dpad, ty, tx, acc);
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int k = k0 + tx * TN + j;
-        if (k < kb) {
-#pragma unroll
-          for (int i = 0; i < TM; ++i)
-            if (acc[i][j] > best_v[i]) best_v[i] = acc[i][j], best_k[i] = k;
+      if (it == 0) {
+        if (tid < tile.rows) s_lab[tid] = p.labels_in[tile.row0 + tid];
+        __syncthreads();
+      } else {
+        assign_tile(p, p.sums + (size_t)(it - 1) * per_iter + img, kb, At, Bt, s_lab);
+        if (it == p.iterations && tid < tile.rows) {
+          if (p.labels_out) p.labels_out[tile.row0 + tid] = s_lab[tid];
+          if (p.labels_out64) p.labels_out64[tile.row0 + tid] = s_lab[tid];
         }
       }
+      if (it < p.iterations)
+        accumulate_tile(p, tile, At, s_lab, p.sums + (size_t)it * per_iter + img);
     }
-    // argmax across the 16 column lanes; ties keep the lowest index (torch.argmax)
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best_v[i], o);
-        const int ok = __shfl_xor_sync(0xffffffffu, best_k[i], o);
-        if (ov > best_v[i] || (ov == best_v[i] && ok < best_k[i])) best_v[i] = ov, best_k[i] = ok;
-      }
-      if (tx == 0) s_lab[ty * TM + i] = best_k[i];
-    }
-    __syncthreads();
-    if (tid < rows) {
-      if (p.labels_out) p.labels_out[row0 + tid] = s_lab[tid];
-      if (p.labels_out64) p.labels_out64[row0 + tid] = s_lab[tid];
-    }
-  } else {
-    if (tid < rows) s_lab[tid] = p.labels_in[row0 + tid];
-    __syncthreads();
+    if (it < p.iterations) grid_barrier(p.barrier, (unsigned)(it + 1) * gridDim.x);
   }
+}
 
-  if (p.sums_out) {
-    // Run-length segment sum: thread (group, d) walks its rows in order and flushes a
-    // fixed-point run total whenever the label changes.
-    const int groups = max(1, kGemmThreads / p.dim);
-    const int g = tid / p.dim, d = tid % p.dim;
-    if (g < groups) {
-      const int per = (rows + groups - 1) / groups;
-      const int r0 = g * per, r1 = min(rows, r0 + per);
-      int run_lab = -1;
-      long long run = 0;
-      for (int r = r0; r < r1; ++r) {
-        const int lab = s_lab[r];
-        if (lab != run_lab) {
-          if (run_lab >= 0)
-            atomic_add_i64(&p.sums_out[((int64_t)b * p.num_clusters + run_lab) * p.dim + d], run);
-          run = 0;
-          run_lab = lab;
-        }
-        run += to_fixed(At[d * LDA + r], p.poison);
-      }
-      if (run_lab >= 0)
-        atomic_add_i64(&p.sums_out[((int64_t)b * p.num_clusters + run_lab) * p.dim + d], run);
-    }
-  }
+// A5 alone: one tile per CTA against ready prototypes.
+__global__ void __launch_bounds__(kGemmThreads) nearest_prototype_kernel(KmeansArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  float* At = smem;
+  float* Bt = At + (size_t)p.dpad * LDA;
+  __shared__ int s_lab[BM];
+  Tile tile;
+  if (!tile_of(p, blockIdx.x, tile)) return;
+  load_rows_transposed<BM, LDA>(At, p.x, p.dim, nullptr, tile.row0, tile.rows, p.dim, p.dpad);
+  assign_tile(p, nullptr, p.num_clusters, At, Bt, s_lab);
+  if (threadIdx.x < tile.rows) p.labels_out64[tile.row0 + threadIdx.x] = s_lab[threadIdx.x];
 }
 
 __global__ void copy_labels_kernel(const int32_t* in, int64_t n, int32_t* out, int64_t* out64) {
@@ -147,17 +252,6 @@ __global__ void copy_labels_kernel(const int32_t* in, int64_t n, int32_t* out, i
 
 static size_t kmeans_smem_bytes(int dpad) {
   return (size_t)dpad * (LDA + LDB) * sizeof(float);
-}
-
-static int launch_step(const KmeansStep& s, int batch, int max_rows_per_image,
-                       cudaStream_t st) {
-  const size_t smem = kmeans_smem_bytes(s.dpad);
-  SPML_CUDA(cudaFuncSetAttribute(kmeans_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-  dim3 grid((unsigned)ceil_div(max_rows_per_image, BM), (unsigned)batch);
-  kmeans_step_kernel<<<grid, kGemmThreads, smem, st>>>(s);
-  SPML_LAUNCH_CHECK("kmeans_step_kernel");
-  return SPML_OK;
 }
 
 }  // namespace spml
@@ -178,7 +272,6 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
                      dim > 0 && num_clusters > 0 && iterations >= 0 && max_rows_per_image >= 0,
                  "kmeans: bad arguments");
   SPML_CHECK_SUPPORTED(dim <= SPML_MAX_DIM, "kmeans: dim %d exceeds %d", dim, SPML_MAX_DIM);
-  SPML_CHECK_SUPPORTED(batch <= 65535, "kmeans: batch %d exceeds 65535", batch);
   cudaStream_t st = as_stream(stream);
   if (max_rows_per_image == 0) return SPML_OK;
   if (iterations == 0) {
@@ -196,28 +289,40 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
     return SPML_E_WORKSPACE;
   }
   SPML_CUDA(cudaMemsetAsync(workspace, 0, need, st));
-  int* poison = reinterpret_cast<int*>(workspace);
-  long long* sums = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 16);
-  const size_t per_iter = (size_t)batch * num_clusters * dim;
 
-  KmeansStep s{};
-  s.x = x;
-  s.img_off = img_off;
-  s.dim = dim;
-  s.dpad = pad4(dim);
-  s.num_clusters = num_clusters;
-  s.k_per_image = k_per_image;
-  s.poison = poison;
-  s.eps = 1e-12f;
-  for (int t = 0; t <= iterations; ++t) {
-    s.sums_in = t > 0 ? sums + (size_t)(t - 1) * per_iter : nullptr;
-    s.sums_out = t < iterations ? sums + (size_t)t * per_iter : nullptr;
-    s.labels_in = t == 0 ? init_labels : nullptr;
-    s.labels_out = t == iterations ? labels_out : nullptr;
-    s.labels_out64 = t == iterations ? labels_out_i64 : nullptr;
-    const int rc = launch_step(s, batch, max_rows_per_image, st);
-    if (rc != SPML_OK) return rc;
-  }
+  KmeansArgs p{};
+  p.x = x;
+  p.img_off = img_off;
+  p.batch = batch;
+  p.tiles_per_img = (int)ceil_div(max_rows_per_image, BM);
+  p.dim = dim;
+  p.dpad = pad4(dim);
+  p.num_clusters = num_clusters;
+  p.k_per_image = k_per_image;
+  p.poison = reinterpret_cast<int*>(workspace);
+  p.barrier = reinterpret_cast<unsigned*>(workspace) + 1;
+  p.sums = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 16);
+  p.iterations = iterations;
+  p.labels_in = init_labels;
+  p.labels_out = labels_out;
+  p.labels_out64 = labels_out_i64;
+  p.eps = 1e-12f;
+
+  const size_t smem = kmeans_smem_bytes(p.dpad);
+  SPML_CUDA(cudaFuncSetAttribute(kmeans_persistent_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int device = 0, sms = 0, per_sm = 0;
+  SPML_CUDA(cudaGetDevice(&device));
+  SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  SPML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_persistent_kernel,
+                                                          kGemmThreads, smem));
+  SPML_CHECK_SUPPORTED(per_sm >= 1, "kmeans: kernel does not fit on an SM (dim %d)", dim);
+  const int64_t tiles = (int64_t)batch * p.tiles_per_img;
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
+  void* args[] = {&p};
+  SPML_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kmeans_persistent_kernel),
+                                        dim3(grid), dim3(kGemmThreads), args, smem, st));
+  SPML_LAUNCH_CHECK("kmeans_persistent_kernel");
   return SPML_OK;
 }
 
@@ -230,16 +335,23 @@ int spml_nearest_prototype(const float* x, int64_t rows, int dim, const float* p
                        SPML_MAX_DIM);
   SPML_CHECK_SUPPORTED(rows < (1ll << 31), "nearest_prototype: too many rows");
   if (rows == 0) return SPML_OK;
-  KmeansStep s{};
-  s.x = x;
-  s.rows_total = rows;
-  s.dim = dim;
-  s.dpad = pad4(dim);
-  s.num_clusters = num_protos;
-  s.protos_in = protos;
-  s.labels_out64 = out;
-  s.eps = 1e-12f;
-  return launch_step(s, 1, (int)rows, as_stream(stream));
+  KmeansArgs p{};
+  p.x = x;
+  p.rows_total = rows;
+  p.batch = 1;
+  p.tiles_per_img = (int)ceil_div(rows, BM);
+  p.dim = dim;
+  p.dpad = pad4(dim);
+  p.num_clusters = num_protos;
+  p.protos_in = protos;
+  p.labels_out64 = out;
+  p.eps = 1e-12f;
+  const size_t smem = kmeans_smem_bytes(p.dpad);
+  SPML_CUDA(cudaFuncSetAttribute(nearest_prototype_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nearest_prototype_kernel<<<(unsigned)p.tiles_per_img, kGemmThreads, smem, as_stream(stream)>>>(p);
+  SPML_LAUNCH_CHECK("nearest_prototype_kernel");
+  return SPML_OK;
 }
 
 }  // extern "C"

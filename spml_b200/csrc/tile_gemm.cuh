@@ -21,19 +21,44 @@ constexpr int LDB = BN + 4;
 
 __host__ __device__ inline int pad4(int d) { return (d + 3) & ~3; }
 
+constexpr int kMaxSlots = (SPML_MAX_DIM + 31) / 32;   // 32-channel slots per lane
+
 // T[d * LD + r] = src[row(r)][d] for r < RMAX, d < dpad; zero for r >= rows or d >= dim.
-// row(r) = row_index ? row_index[row0 + r] : row0 + r.  One warp per row, lanes
-// across d (coalesced global reads).
+// row(r) = row_index ? row_index[row0 + r] : row0 + r.  One warp per row, lanes across d
+// (coalesced global reads); eight rows are fetched into registers before anything is
+// stored so that the loads of a warp are all in flight together.
 template <int RMAX, int LD>
 __device__ __forceinline__ void load_rows_transposed(float* T, const float* __restrict__ src,
                                                      int64_t ld_src,
                                                      const int32_t* __restrict__ row_index,
                                                      int64_t row0, int rows, int dim, int dpad) {
+  constexpr int kWarps = kGemmThreads / 32;
+  constexpr int kBatch = 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < RMAX; r += kGemmThreads / 32) {
-    const float* rp = nullptr;
-    if (r < rows) rp = src + (row_index ? (int64_t)row_index[row0 + r] : row0 + r) * ld_src;
-    for (int d = lane; d < dpad; d += 32) T[d * LD + r] = (rp && d < dim) ? rp[d] : 0.f;
+  for (int rb = warp; rb < RMAX; rb += kWarps * kBatch) {
+    float v[kBatch][kMaxSlots];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int r = rb + i * kWarps;
+      const float* rp = nullptr;
+      if (r < rows) rp = src + (row_index ? (int64_t)row_index[row0 + r] : row0 + r) * ld_src;
+#pragma unroll
+      for (int s = 0; s < kMaxSlots; ++s) {
+        const int d = lane + 32 * s;
+        v[i][s] = (rp && d < dim) ? rp[d] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int r = rb + i * kWarps;
+      if (r < RMAX) {
+#pragma unroll
+        for (int s = 0; s < kMaxSlots; ++s) {
+          const int d = lane + 32 * s;
+          if (d < dpad) T[d * LD + r] = v[i][s];
+        }
+      }
+    }
   }
 }
 

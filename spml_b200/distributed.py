@@ -1,0 +1,95 @@
+"""Rank plumbing for the data-parallel deployment: one process per GPU, the minibatch
+sharded over images, no data-path collective.
+
+The reference runs single-process `DataParallel` with a gather of every pixel embedding
+to an anchor GPU (spml/models/utils.py:86-127).  Here each rank owns its images end to
+end; the only collective of a training step is the backbone's gradient all-reduce
+(`all_reduce_gradients`, what DDP does), and timings are reduced with a max over ranks.
+Works with the `nccl` backend on GPUs and `gloo` on CPUs (used by the tests).
+"""
+
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+  """(rank, world_size, local_rank) from the torchrun environment; (0, 1, 0) without it."""
+  return (int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')),
+          int(os.environ.get('LOCAL_RANK', '0')))
+
+
+def init(backend=None):
+  """Initialises the default process group when launched under torchrun."""
+  rank, size, local_rank = world()
+  if size > 1 and not dist.is_initialized():
+    if backend is None:
+      backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    kwargs = {}
+    if backend == 'nccl':
+      torch.cuda.set_device(local_rank)
+      kwargs['device_id'] = torch.device('cuda', local_rank)
+    dist.init_process_group(backend, **kwargs)
+  return rank, size, local_rank
+
+
+def shard_images(num_images, rank, world_size):
+  """Contiguous, balanced [begin, end) range of a global batch owned by `rank`
+  (the reference gives every GPU its own DataLoader batch, others.py:62-71)."""
+  base, extra = divmod(num_images, world_size)
+  begin = rank * base + min(rank, extra)
+  return begin, begin + base + (1 if rank < extra else 0)
+
+
+def batch_index_offset(images_per_rank, rank):
+  """Global index of a rank's first image: what `N * gpu_id` is in common.py:376-377."""
+  return images_per_rank * rank
+
+
+def max_over_ranks(value, device=None):
+  """Max of a python float over all ranks (device-side timing is the max over ranks)."""
+  if not dist.is_initialized() or dist.get_world_size() == 1:
+    return float(value)
+  t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return float(t[0])
+
+
+def sum_over_ranks(value, device=None):
+  if not dist.is_initialized() or dist.get_world_size() == 1:
+    return float(value)
+  t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  return float(t[0])
+
+
+def all_reduce_gradients(parameters, bucket_bytes=64 << 20):
+  """One bucketed all-reduce (mean) of the gradients of `parameters`: the single
+  collective of a step.  NVSwitch makes the cost latency- not link-bound, so the
+  buckets are large."""
+  if not dist.is_initialized() or dist.get_world_size() == 1:
+    return 0
+  size = dist.get_world_size()
+  grads = [p.grad for p in parameters if p.grad is not None]
+  buckets, cur, cur_bytes = [], [], 0
+  for g in grads:
+    nbytes = g.numel() * g.element_size()
+    if cur and (cur_bytes + nbytes > bucket_bytes or g.dtype != cur[0].dtype):
+      buckets.append(cur)
+      cur, cur_bytes = [], 0
+    cur.append(g)
+    cur_bytes += nbytes
+  if cur:
+    buckets.append(cur)
+  for bucket in buckets:
+    flat = torch.cat([g.reshape(-1) for g in bucket])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(size)
+    off = 0
+    for g in bucket:
+      g.copy_(flat[off:off + g.numel()].view_as(g))
+      off += g.numel()
+  return len(buckets)

@@ -1,0 +1,63 @@
+"""World-size-2 gloo tests of the rank plumbing (CPU, no kernels)."""
+
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spml_b200 import distributed as D
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(('127.0.0.1', 0))
+    return s.getsockname()[1]
+
+
+def _worker(rank, size, port, out):
+  os.environ.update(RANK=str(rank), WORLD_SIZE=str(size), LOCAL_RANK=str(rank),
+                    MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  r, s, _ = D.init('gloo')
+  assert (r, s) == (rank, size)
+  lo, hi = D.shard_images(7, rank, size)
+  mx = D.max_over_ranks(10.0 + rank)
+  total = D.sum_over_ranks(hi - lo)
+  w1 = torch.nn.Parameter(torch.zeros(3, 5))
+  w2 = torch.nn.Parameter(torch.zeros(11))
+  w1.grad = torch.full((3, 5), float(rank + 1))
+  w2.grad = torch.arange(11, dtype=torch.float32) * (rank + 1)
+  buckets = D.all_reduce_gradients([w1, w2], bucket_bytes=32)
+  ok = (torch.allclose(w1.grad, torch.full((3, 5), 1.5)) and
+        torch.allclose(w2.grad, torch.arange(11, dtype=torch.float32) * 1.5))
+  out[rank] = (lo, hi, mx, total, buckets, ok, D.batch_index_offset(4, rank))
+  dist.destroy_process_group()
+
+
+def test_two_rank_plumbing():
+  size, port = 2, _free_port()
+  with mp.Manager() as m:
+    out = m.dict()
+    mp.spawn(_worker, args=(size, port, out), nprocs=size, join=True)
+    r0, r1 = out[0], out[1]
+  assert (r0[0], r0[1], r1[0], r1[1]) == (0, 4, 4, 7)        # shards tile the batch
+  assert r0[2] == r1[2] == 11.0 and r0[3] == r1[3] == 7.0
+  assert r0[4] == r1[4] == 2 and r0[5] and r1[5]
+  assert (r0[6], r1[6]) == (0, 4)
+
+
+def test_shards_cover_any_batch():
+  for n in range(0, 40):
+    for w in (1, 2, 3, 4, 8):
+      spans = [D.shard_images(n, r, w) for r in range(w)]
+      assert spans[0][0] == 0 and spans[-1][1] == n
+      assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+      assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_single_process_is_identity():
+  assert D.world() == (int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)),
+                       int(os.environ.get('LOCAL_RANK', 0)))
+  assert D.max_over_ranks(3.5) == 3.5 and D.sum_over_ranks(2.0) == 2.0
+  assert D.all_reduce_gradients([]) == 0

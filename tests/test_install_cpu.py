@@ -1,0 +1,43 @@
+"""install() rebinds the reference's symbols (only where the reference is importable:
+the build container; the GPU box has no /root/reference)."""
+
+import importlib
+import os
+import sys
+
+import pytest
+
+REF = '/root/reference'
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'spml')), reason='reference not present')
+def test_install_rebinds_and_uninstall_restores():
+  sys.path.insert(0, REF)
+  try:
+    import spml_b200
+    inst = importlib.import_module('spml_b200.install')
+    common = importlib.import_module('spml.utils.segsort.common')
+    loss = importlib.import_module('spml.utils.segsort.loss')
+    orig_fn, orig_cls = common.segment_by_kmeans, loss.SegSortLoss
+    done = spml_b200.install()
+    assert 'spml.utils.segsort.common.segment_by_kmeans' in done
+    assert common.segment_by_kmeans is spml_b200.segsort_common.segment_by_kmeans
+    assert loss.SegSortLoss is spml_b200.segsort_loss.SegSortLoss
+    # the reference's own call sites resolve through the module attribute
+    pred = importlib.import_module('spml.models.predictions.segsort')
+    assert pred.segsort_loss.SegSortLoss is spml_b200.segsort_loss.SegSortLoss
+    assert pred.Segsort is spml_b200.predictions.Segsort
+    spml_b200.uninstall()
+    assert common.segment_by_kmeans is orig_fn and loss.SegSortLoss is orig_cls
+    assert len(inst.BINDINGS) == 7
+  finally:
+    sys.path.remove(REF)
+    for k in [k for k in sys.modules if k == 'spml' or k.startswith('spml.')]:
+      del sys.modules[k]
+
+
+def test_binding_table_names_exist_in_package():
+  inst = importlib.import_module('spml_b200.install')
+  for mod, attrs in inst.BINDINGS.items():
+    for name, repl in attrs.items():
+      assert callable(repl), (mod, name)
