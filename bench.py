@@ -169,31 +169,63 @@ def workload_config(w, n_gpus):
 # ------------------------------------------------------------------------------ our arm
 
 
-def algorithmic_bytes(name, shapes):
-  """Algorithmic HBM bytes of one call of an entry point (SURVEY.md section 8d formulas,
-  fp32 embeddings: b_e = 4)."""
-  n, d, dl, m, k, t = (shapes[x] for x in ('n', 'd', 'dl', 'm_all', 'k', 't'))
+def algorithmic_work(key, sh):
+  """(bytes, flops) of ONE call of a profiled entry point: SURVEY.md section 8d formulas with
+  fp32 embeddings in HBM (b_e = 4).  `key` is 'entry' or 'entry:problem'."""
+  name, _, prob = key.partition(':')
+  d, dl, k, t = sh['d'], sh['dl'], sh['k'], sh['t']
+  n = sh['n']
   if name == 'spml_kmeans':
-    return (t + 1) * n * dl * 4 + t * n * 4 + 2 * t * k * dl * 4
+    return ((t + 1) * n * dl * 4 + t * n * 4 + 2 * t * k * dl * 4, t * (2 * n * k * dl + n * dl))
   if name == 'spml_normalize_pack_fwd':
-    return n * d * 4 + n * (d + dl) * 4 + n * 32
+    return (sh['cap'] * d * 4 + n * (d + dl) * 4 + n * 32, 6 * n * dl)
   if name == 'spml_normalize_pack_bwd':
-    return n * (2 * d + 2 * dl) * 4 + n * d * 4
-  if name == 'spml_segsort_fwd':
-    return n * (d * 4 + 24 + 12) + m * d * 4
-  if name == 'spml_segsort_bwd':
-    return n * (2 * d * 4 + d * 4 + 24 + 12) + 3 * m * d * 4
+    return (n * (2 * d + 2 * dl) * 4 + sh['cap'] * d * 4, 8 * n * dl)
+  if name in ('spml_segsort_fwd', 'spml_segsort_bwd'):
+    rows, cols, dim = {'sem_ann': (sh['n_lab'], sh['m_lab'], d), 'sem_occ': (n, sh['m_all'], d),
+                       'img_sim': (n, sh['m_cur'] / max(sh['batch'], 1), dl)}.get(
+                           prob, (n, sh['m_all'], d))
+    if name == 'spml_segsort_fwd':
+      return (rows * (dim * 4 + 36) + cols * dim * 4, 2 * rows * cols * dim)
+    return (rows * (2 * dim * 4 + dim * 4 + 36) + 3 * cols * dim * 4, 6 * rows * cols * dim)
   if name == 'spml_segment_prototypes_fwd':
-    return n * d * 4 + n * 8 + 3 * m * d * 4
+    return (n * d * 4 + n * 8 + 3 * sh['m_cur'] * d * 4, 2 * n * d)
   if name == 'spml_segment_prototypes_bwd':
-    return n * d * 4 + n * 8 + 2 * m * d * 4
-  return None
+    return (n * d * 4 + n * 8 + 2 * sh['m_cur'] * d * 4, 4 * n * d)
+  if name == 'spml_topk_ranking':
+    return (2 * sh['m_all'] * d * 4, 2 * sh['m_all'] * sh['m_all'] * d)
+  return (None, None)
+
+
+def roofline_of(key, sh, ms_per_call, launches_per_call, peaks):
+  """Roofline of one profiled call: the bound is whichever of HBM / tensor time is larger."""
+  nbytes, flops = algorithmic_work(key, sh)
+  if nbytes is None:
+    return None
+  t_hbm = nbytes / (peaks['hbm_gbs'] * 1e9)
+  tensor = key.startswith('spml_segsort')     # the only tensor-core kernels of the path
+  t_tc = flops / (peaks['bf16_tflops'] * 1e12) if tensor else 0.0
+  sec = ms_per_call * 1e-3
+  if t_tc > t_hbm:
+    achieved = flops / sec / 1e12
+    out = {'bound': 'tensor', 'achieved': round(achieved, 3), 'peak': peaks['bf16_tflops'],
+           'unit': 'TFLOP/s', 'frac': round(achieved / peaks['bf16_tflops'], 5)}
+  else:
+    achieved = nbytes / sec / 1e9
+    out = {'bound': 'hbm', 'achieved': round(achieved, 2), 'peak': peaks['hbm_gbs'],
+           'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 5)}
+  out.update({'kernel': key, 'traffic': None, 'peak_source': peaks['source'],
+              'algorithmic_bytes_per_call': int(nbytes), 'algorithmic_flops_per_call': int(flops),
+              'ms_per_call': round(ms_per_call, 4), 'launches_per_call': launches_per_call,
+              'roofline_ms_per_call': round(1e3 * max(t_hbm, t_tc), 5)})
+  return out
 
 
 def run_b200(args):
   import torch.distributed as dist
   from spml_b200 import _lib
   from spml_b200.head import ContrastiveHead
+  from spml_b200.static_head import StaticContrastiveHead
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -208,7 +240,9 @@ def run_b200(args):
 
   w = synth.WORKLOADS[args.workload]
   cfg = synth.make_config(w)
-  head = ContrastiveHead(cfg).to(dev)
+  # the product path: fixed-capacity head, forward + backward + bank update as one CUDA graph
+  head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels, device=dev)
+  dyn_head = ContrastiveHead(cfg).to(dev)     # reference-shaped drop-in API, timed for comparison
 
   # every rank gets its own minibatches (different seeds): weak scaling over images
   host = [synth.make_batch(w, seed=235 + rank, step=s) for s in range(POOL)]
@@ -220,27 +254,27 @@ def run_b200(args):
   loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
   d2h_bytes = grad_host.numel() * 4 + loss_host.numel() * 4
 
+  def args_of(b):
+    return (b['embedding'], b['semantic_label'], b['instance_label'], b['semantic_tag'],
+            b['local_feature'])
+
   def step_resident(i):
-    b = resident[i % POOL]
-    emb = b['embedding'].detach().requires_grad_(True)
-    out = head(emb, b['semantic_label'], b['instance_label'], b['semantic_tag'],
-               b['local_feature'])
-    out['loss'].backward()
-    head.update_memory_bank(world)
-    return out, emb.grad
+    return head.step(*args_of(resident[i % POOL]))
 
   def step_e2e(i):
-    hb = host[i % POOL]
-    b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-    emb = b['embedding'].requires_grad_(True)
-    out = head(emb, b['semantic_label'], b['instance_label'], b['semantic_tag'],
-               b['local_feature'])
+    out = head.step(*args_of(host[i % POOL]))          # pinned host -> device inside the step
+    grad_host.copy_(out['grad_embedding'], non_blocking=True)
+    loss_host.copy_(torch.stack([out['sem_ann_loss'], out['sem_occ_loss'], out['img_sim_loss'],
+                                 out['accuracy']]), non_blocking=True)
+    return out
+
+  def step_drop_in(i):
+    b = resident[i % POOL]
+    emb = b['embedding'].detach().requires_grad_(True)
+    out = dyn_head(emb, b['semantic_label'], b['instance_label'], b['semantic_tag'],
+                   b['local_feature'])
     out['loss'].backward()
-    head.update_memory_bank(world)
-    grad_host.copy_(emb.grad, non_blocking=True)
-    loss_host.copy_(torch.stack([out['sem_ann_loss'].detach(), out['sem_occ_loss'].detach(),
-                                 out['img_sim_loss'].detach(), out['accuracy']]),
-                    non_blocking=True)
+    dyn_head.update_memory_bank(1)
     return out
 
   def barrier():
@@ -252,7 +286,8 @@ def run_b200(args):
   def timed(step_fn, steps, warmup):
     """Per-step CUDA-event timing on the launching stream with an L2 flush (untimed)
     between steps; returns the summed milliseconds of `steps` steps."""
-    head.memory_banks.clear()
+    head.reset_memory_bank()
+    dyn_head.memory_banks.clear()
     for i in range(warmup):
       step_fn(i)
     barrier()
@@ -275,9 +310,15 @@ def run_b200(args):
   if sampler:
     sampler.start()
     time.sleep(0.3)
-  ms_res, launches, wall_res = timed(step_resident, args.steps, max(args.warmup, 3))
+  step_resident(0)                       # builds the graph (untimed)
+  torch.cuda.synchronize()
+  kernels_per_step = head.kernels_per_step
+  ms_res, _, wall_res = timed(step_resident, args.steps, max(args.warmup, 3))
   ms_e2e, _, wall_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
   clocks = sampler.stop() if sampler else None
+  ms_dyn, _, _ = timed(step_drop_in, max(3, args.steps // 3), 3)
+  ms_dyn = ms_dyn / max(3, args.steps // 3)
+  launches = kernels_per_step * args.steps
 
   def max_over_ranks(x):
     if world == 1:
@@ -292,15 +333,17 @@ def run_b200(args):
   # ---- per-entry-point profile of a few steps (separate pass; events per C-ABI call)
   roofline, breakdown = None, None
   if rank == 0:
-    head.memory_banks.clear()
+    prof_head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels,
+                                      device=dev, use_graph=False)
+    prof_head.collect_stats = True
     for i in range(3):
-      step_resident(i)
+      prof_head.step(*args_of(resident[i % POOL]))
     torch.cuda.synchronize()
     _lib.PROFILE = []
     prof_steps = 5
     for i in range(prof_steps):
       flush.fill_(i)
-      out, _ = step_resident(3 + i)
+      out = prof_head.step(*args_of(resident[(3 + i) % POOL]))
     torch.cuda.synchronize()
     records, _lib.PROFILE = _lib.PROFILE, None
     agg = {}
@@ -315,24 +358,24 @@ def run_b200(args):
                      'kernels_per_step': v['kernels'] / prof_steps,
                      'share': round(v['ms'] / total_ms, 4)}
                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])}
-    top = next(iter(breakdown))
-    n_rows = out['datas']['cluster_index'].shape[0]
-    m_cur = out['targets']['prototype'].shape[0]
-    m_all = m_cur * (1 + len(head.memory_banks.get('memory_prototype', [])))
-    shapes = {'n': n_rows, 'd': w.dim, 'dl': w.dim + w.loc_channels, 'm_all': m_all,
+    n_rows = int(out['num_pixels'])
+    shapes = {'n': n_rows, 'cap': w.batch * w.height * w.width, 'batch': w.batch, 'd': w.dim,
+              'dl': w.dim + w.loc_channels, 'm_cur': int(out['num_segments']),
+              'm_all': int(out['num_live_prototypes']), 'm_lab': int(out['num_labelled_prototypes']),
+              'n_lab': int(out['num_labelled_pixels']),
               'k': w.num_clusters[0] * w.num_clusters[1], 't': w.iterations}
     peaks = load_peaks()
-    alg = algorithmic_bytes(top, shapes)
-    call_ms = agg[top]['ms'] / agg[top]['calls']
-    if alg is not None:
-      achieved = alg / (call_ms * 1e-3) / 1e9
-      roofline = {'kernel': top, 'bound': 'hbm', 'achieved': round(achieved, 2),
-                  'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                  'frac': round(achieved / peaks['hbm_gbs'], 5), 'traffic': None,
-                  'peak_source': peaks['source'],
-                  'algorithmic_bytes_per_call': alg, 'ms_per_call': round(call_ms, 4),
-                  'launches_per_call': agg[top]['kernels'] / agg[top]['calls'],
-                  'shapes': shapes}
+    per_kernel = {}
+    for key, a in agg.items():
+      r = roofline_of(key, shapes, a['ms'] / a['calls'], a['kernels'] / a['calls'], peaks)
+      if r is not None:
+        per_kernel[key] = r
+    top = next(k for k in breakdown if k in per_kernel)
+    roofline = dict(per_kernel[top])
+    roofline['shapes'] = shapes
+    roofline['all'] = {k: {'bound': v['bound'], 'frac': v['frac'], 'ms_per_call': v['ms_per_call'],
+                           'roofline_ms_per_call': v['roofline_ms_per_call']}
+                       for k, v in per_kernel.items()}
 
   # ---- CPU baseline (oracle port) on this box's host cores, rank 0, N == 1 only
   cpu_baseline = None
@@ -371,7 +414,9 @@ def run_b200(args):
                 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': d2h_bytes},
         'gpu_launches': launches,
-        'gpu_launches_per_step': launches / args.steps,
+        'gpu_launches_per_step': kernels_per_step,
+        'cuda_graph': True,
+        'drop_in_api_ms_per_step': ms_dyn,
         'wall_s': {'resident': round(wall_res, 4), 'e2e': round(wall_e2e, 4)},
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'breakdown': breakdown,

@@ -44,8 +44,8 @@ extern "C" {
 const char* spml_last_error(void);
 /* ABI version, bumped on any signature change. */
 int spml_abi_version(void);
-/* diagnostics: number of kernels this library has launched from the calling
- * thread since it was loaded (memsets are not counted). */
+/* diagnostics: number of kernels this library has launched (all threads) since it
+ * was loaded (memsets are not counted). */
 uint64_t spml_debug_launch_count(void);
 
 /* ---------------------------------------------------------------------------
@@ -152,16 +152,32 @@ int spml_unique_inverse(const int64_t* hi, const int64_t* lo, int64_t n,
  *     |x| <= 1024 (they are unit vectors on this path); a violation (or a NaN)
  *     turns every prototype of the call into NaN.
  *     bwd: dx[i] = beta*dx[i] + (dp - p (p.dp)) / ||sum||  gathered at seg[i].
+ *     rows_dev (nullable, device) holds the live row count when it only exists on the
+ *     device; rows is then the capacity.
  *     workspace: spml_segment_prototypes_workspace_bytes(m, dim).
  */
 size_t spml_segment_prototypes_workspace_bytes(int64_t m, int dim);
-int spml_segment_prototypes_fwd(const float* x, int64_t rows, int dim, const int64_t* seg,
-                                int64_t m, float eps, float* protos, float* norms,
-                                void* workspace, size_t workspace_bytes, void* stream);
+int spml_segment_prototypes_fwd(const float* x, int64_t rows, const int32_t* rows_dev, int dim,
+                                const int64_t* seg, int64_t m, float eps, float* protos,
+                                float* norms, void* workspace, size_t workspace_bytes,
+                                void* stream);
 int spml_segment_prototypes_bwd(const float* dprotos, const float* protos,
                                 const float* norms, const int64_t* seg, int64_t rows,
-                                int dim, int64_t m, float eps, float beta, float* dx,
-                                void* stream);
+                                const int32_t* rows_dev, int dim, int64_t m, float eps,
+                                float beta, float* dx, void* stream);
+
+/* B1 (shortcut). spml/models/utils.py:100-111 when the segment ids come straight from
+ *     segment_by_kmeans (dense ranks of (image, cluster, label)): decodes the packed
+ *     labels per pixel (sem = label / divisor, inst = label % divisor, keep = live &&
+ *     sem < num_classes) and scatters them to the segments (p_sem, p_inst, p_batch,
+ *     p_live; capacity m_cap).  Rows >= *rows_dev are padding.  Segments nobody maps to
+ *     get p_sem = dead_label, p_batch = -1, p_live = 0.  A segment id >= m_cap sets
+ *     overflow[0] = 1 (never reset here) and is skipped. */
+int spml_segment_labels(const int64_t* labels, const int64_t* batch, const int64_t* seg,
+                        int64_t cap, const int32_t* rows_dev, int64_t divisor,
+                        int64_t num_classes, int64_t m_cap, int64_t dead_label, int64_t* sem,
+                        int64_t* inst, int64_t* keep, int64_t* p_sem, int64_t* p_inst,
+                        int64_t* p_batch, uint8_t* p_live, int32_t* overflow, void* stream);
 
 /* ---------------------------------------------------------------------------
  * C1 / C2. spml/utils/segsort/loss.py:15-130 (+ SegSortLoss / SetSegSortLoss
@@ -240,12 +256,14 @@ int spml_pack_tags(const int64_t* tags, int64_t rows, int cols, int64_t ld,
  * C3. spml/utils/segsort/eval.py:9-52 top_k_ranking: for each query row the k
  *     prototypes of largest q.p (descending, lowest index first on ties);
  *     topk_labels[q, r] = plab[index]; hit_count[0] = number of (q, r) with
- *     qlab[q] == plab[index] (accuracy = hit_count / (nq * k)).
+ *     qlab[q] == plab[index], hit_count[1] = number of queries that took part
+ *     (accuracy = hit_count[0] / (hit_count[1] * k)).  qvalid / pvalid (nullable byte
+ *     masks) drop query rows / prototype columns, for fixed-capacity buffers.
  */
 int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int dim,
-                      const int64_t* qlab, const int64_t* plab, int k,
-                      int64_t* topk_labels, int64_t* topk_index, int32_t* hit_count,
-                      void* stream);
+                      const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
+                      const uint8_t* pvalid, int k, int64_t* topk_labels,
+                      int64_t* topk_index, int32_t* hit_count, void* stream);
 
 #ifdef __cplusplus
 }

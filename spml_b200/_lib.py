@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libspml_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
@@ -60,18 +60,21 @@ SIGNATURES = {
     'spml_unique_inverse': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp, c_sz, c_vp]),
     'spml_segment_prototypes_workspace_bytes': (c_sz, [c_i64, c_i32]),
-    'spml_segment_prototypes_fwd': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_f32,
+    'spml_segment_prototypes_fwd': (ctypes.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_i64, c_f32,
                                                    c_vp, c_vp, c_vp, c_sz, c_vp]),
-    'spml_segment_prototypes_bwd': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32,
+    'spml_segment_prototypes_bwd': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32,
                                                    c_i64, c_f32, c_f32, c_vp, c_vp]),
+    'spml_segment_labels': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64,
+                                           c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp]),
     'spml_segsort_workspace_bytes': (c_sz, [ctypes.POINTER(SegsortDesc)]),
     'spml_segsort_fwd': (ctypes.c_int, [ctypes.POINTER(SegsortDesc), c_vp, c_vp, c_vp, c_vp,
                                         c_sz, c_vp]),
     'spml_segsort_bwd': (ctypes.c_int, [ctypes.POINTER(SegsortDesc), c_vp, c_vp, c_f32, c_vp,
                                         c_i64, c_vp, c_vp, c_sz, c_vp]),
     'spml_pack_tags': (ctypes.c_int, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
-    'spml_topk_ranking': (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32,
-                                         c_vp, c_vp, c_vp, c_vp]),
+    'spml_topk_ranking': (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                         c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lock = threading.Lock()
@@ -106,6 +109,7 @@ def load():
 # bench.py sets this to a list to collect (entry point, start event, end event,
 # kernels launched) for every call; None (the default) costs nothing.
 PROFILE = None
+PROFILE_TAG = ''     # appended to the entry-point name of profiled calls (e.g. ':sem_occ')
 
 
 def call(name, *args):
@@ -117,7 +121,7 @@ def call(name, *args):
     start.record()
     rc = getattr(lib, name)(*args)
     end.record()
-    PROFILE.append((name, start, end, lib.spml_debug_launch_count() - before))
+    PROFILE.append((name + PROFILE_TAG, start, end, lib.spml_debug_launch_count() - before))
   else:
     rc = getattr(lib, name)(*args)
   if rc != 0:

@@ -14,8 +14,10 @@ constexpr int kSumThreads = 256;
 constexpr int kSumRows = 64;  // rows per CTA
 
 __global__ void __launch_bounds__(kSumThreads)
-segment_sum_kernel(const float* __restrict__ x, int64_t rows, int dim,
+segment_sum_kernel(const float* __restrict__ x, int64_t rows_cap, const int32_t* rows_dev, int dim,
                    const int64_t* __restrict__ seg, int64_t m, long long* sums, int* poison) {
+  const int64_t rows = rows_dev ? min(rows_cap, (int64_t)*rows_dev) : rows_cap;
+  if ((int64_t)blockIdx.x * kSumRows >= rows) return;
   const int groups = max(1, kSumThreads / dim);
   const int g = threadIdx.x / dim, d = threadIdx.x % dim;
   if (g >= groups) return;
@@ -74,10 +76,12 @@ __global__ void prototype_finalize_kernel(const long long* __restrict__ sums,
 __global__ void prototype_bwd_kernel(const float* __restrict__ dprotos,
                                      const float* __restrict__ protos,
                                      const float* __restrict__ norms,
-                                     const int64_t* __restrict__ seg, int64_t rows, int dim,
-                                     int64_t m, float eps, float beta, float* __restrict__ dx) {
+                                     const int64_t* __restrict__ seg, int64_t rows_cap,
+                                     const int32_t* rows_dev, int dim, int64_t m, float eps,
+                                     float beta, float* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t rows = rows_dev ? min(rows_cap, (int64_t)*rows_dev) : rows_cap;
   if (row >= rows) return;
   const int64_t s = seg[row];
   const bool in = s >= 0 && s < m;
@@ -106,8 +110,9 @@ size_t spml_segment_prototypes_workspace_bytes(int64_t m, int dim) {
   return 16 + (size_t)m * dim * sizeof(long long);
 }
 
-int spml_segment_prototypes_fwd(const float* x, int64_t rows, int dim, const int64_t* seg,
-                                int64_t m, float eps, float* protos, float* norms,
+int spml_segment_prototypes_fwd(const float* x, int64_t rows, const int32_t* rows_dev, int dim,
+                                const int64_t* seg, int64_t m, float eps, float* protos,
+                                float* norms,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   using namespace spml;
   SPML_CHECK_ARG(rows >= 0 && m >= 0 && dim > 0, "segment_prototypes_fwd: bad sizes");
@@ -127,7 +132,7 @@ int spml_segment_prototypes_fwd(const float* x, int64_t rows, int dim, const int
   long long* sums = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 16);
   if (rows > 0) {
     segment_sum_kernel<<<(unsigned)ceil_div(rows, kSumRows), kSumThreads, 0, st>>>(
-        x, rows, dim, seg, m, sums, poison);
+        x, rows, rows_dev, dim, seg, m, sums, poison);
     SPML_LAUNCH_CHECK("segment_sum_kernel");
   }
   prototype_finalize_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, st>>>(sums, poison, m, dim, eps,
@@ -137,14 +142,14 @@ int spml_segment_prototypes_fwd(const float* x, int64_t rows, int dim, const int
 }
 
 int spml_segment_prototypes_bwd(const float* dprotos, const float* protos, const float* norms,
-                                const int64_t* seg, int64_t rows, int dim, int64_t m, float eps,
-                                float beta, float* dx, void* stream) {
+                                const int64_t* seg, int64_t rows, const int32_t* rows_dev, int dim,
+                                int64_t m, float eps, float beta, float* dx, void* stream) {
   using namespace spml;
   SPML_CHECK_ARG(rows >= 0 && m >= 0 && dim > 0, "segment_prototypes_bwd: bad sizes");
   if (rows == 0) return SPML_OK;
   SPML_CHECK_ARG(dprotos && protos && norms && seg && dx, "segment_prototypes_bwd: null pointer");
   prototype_bwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(
-      dprotos, protos, norms, seg, rows, dim, m, eps, beta, dx);
+      dprotos, protos, norms, seg, rows, rows_dev, dim, m, eps, beta, dx);
   SPML_LAUNCH_CHECK("prototype_bwd_kernel");
   return SPML_OK;
 }

@@ -205,6 +205,7 @@ struct TcFwdArgs {
   int stages;    // B ring depth (1 or 2)
 };
 
+template <int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1)
 segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
                       const __grid_constant__ CUtensorMap map_el,
@@ -214,7 +215,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
       bar_t_empty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ int32_t s_ccode[2][kTcBN];
+  __shared__ __align__(16) int32_t s_ccode[2][kTcBN];
   __shared__ float s_part[kTcBM][3];
   __shared__ float s_nll[kTcBM];
 
@@ -336,6 +337,8 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
       tc::named_bar_sync(1, kTcEpiThreads);
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
+      const bool tail = c0 + kTcBN > c_end;          // only the last tile has dead columns
+      const int seg_rel = seg_i - c0 - half * 64;    // own segment relative to this half
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
         const int cb = half * 64 + chunk * 32;
@@ -347,16 +350,20 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
         }
+        const int4* codes = reinterpret_cast<const int4*>(&s_ccode[acc][cb]);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int c = c0 + cb + q;
-          const int cc = s_ccode[acc][cb + q];
-          float s = tc::fast_exp2(__uint_as_float(v[q]) * a.kappa_log2e);
-          s = c < c_end ? s : 0.f;
-          const bool match = a.mode == SPML_MODE_TAGS ? (code_i & cc) != 0 : code_i == cc;
-          same += match ? s : 0.f;
-          diff += match ? 0.f : s;
-          self += c == seg_i ? s : 0.f;
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const int4 c4 = codes[q4];
+          const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = q4 * 4 + u;
+            float s = tc::fast_exp2(__uint_as_float(v[q]) * a.kappa_log2e);
+            if (tail) s = c0 + cb + q < c_end ? s : 0.f;
+            const bool match = kMode == SPML_MODE_TAGS ? (code_i & cc[u]) != 0 : code_i == cc[u];
+            if (match) same += s; else diff += s;
+            if (chunk * 32 + q == seg_rel) self += s;
+          }
         }
       }
     }
@@ -440,28 +447,35 @@ struct TcBwdArgs {
   int tmem_cols;
 };
 
-struct PixMeta {              // per-pixel constants of the gradient
-  float inv_num, inv_den, pos, coef;
+// Per-pixel gradient weights.  G_ij = S_ij * w(match_ij, own_ij) with
+//   w = coef ((diff + numset) / den - numset / num),  diff = 1 - match,
+//   numset = pos ? match - own : own        (loss.py:64-80)
+// which only takes four values per pixel.
+struct PixMeta {
+  float w00, w10, w01, w11;   // w[match][own]: w00 = (0,0), w10 = (1,0), w01 = (0,1), w11 = (1,1)
 };
-
-__device__ __forceinline__ float grad_elem(float z, float kl2e, int mode, int code_pix,
-                                           int code_pro, bool own, const PixMeta& pm, bool valid) {
-  const float s = tc::fast_exp2(z * kl2e);
-  const bool match = mode == SPML_MODE_TAGS ? (code_pix & code_pro) != 0 : code_pix == code_pro;
-  const float same = match ? 1.f : 0.f, self = own ? 1.f : 0.f;
-  const float numset = pm.pos != 0.f ? same - self : self;
-  const float g = pm.coef * s * ((1.f - same + numset) * pm.inv_den - numset * pm.inv_num);
-  return valid ? g : 0.f;
-}
 
 __device__ __forceinline__ PixMeta load_pix_meta(const TcBwdArgs& a, int64_t r, float weight) {
   const float* st = a.stats + r * 3;
+  const float inv_num = 1.f / st[0], inv_den = 1.f / st[1];
+  const bool pos = st[2] != 0.f;
+  const float coef = a.d.kappa * (*a.grad_loss) * weight;
   PixMeta pm;
-  pm.inv_num = 1.f / st[0];
-  pm.inv_den = 1.f / st[1];
-  pm.pos = st[2];
-  pm.coef = a.d.kappa * (*a.grad_loss) * weight;
+  pm.w00 = coef * inv_den;
+  pm.w10 = pos ? coef * (inv_den - inv_num) : 0.f;
+  pm.w01 = pos ? coef * inv_num : coef * (2.f * inv_den - inv_num);
+  pm.w11 = pos ? 0.f : coef * (inv_den - inv_num);
   return pm;
+}
+
+template <int kMode>
+__device__ __forceinline__ float grad_elem(float z, float kl2e, int code_pix, int code_pro,
+                                           bool own, const PixMeta& pm) {
+  const float s = tc::fast_exp2(z * kl2e);
+  const bool match = kMode == SPML_MODE_TAGS ? (code_pix & code_pro) != 0 : code_pix == code_pro;
+  const float w_own = match ? pm.w11 : pm.w01;
+  const float w_oth = match ? pm.w10 : pm.w00;
+  return s * (own ? w_own : w_oth);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float x, float y) {
@@ -469,7 +483,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float x, float y) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <bool kProtoOwner>
+template <bool kProtoOwner, int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1)
 segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
                       const __grid_constant__ CUtensorMap map_al,
@@ -479,9 +493,9 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
   __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
       bar_t_empty[2], bar_g_full[2], bar_g_empty[2], bar_d_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ int32_t s_code[2][kBwdBN];
-  __shared__ int32_t s_seg[2][kBwdBN];
-  __shared__ PixMeta s_pm[2][kBwdBN];
+  __shared__ __align__(16) int32_t s_code[2][kBwdBN];
+  __shared__ __align__(16) int32_t s_seg[2][kBwdBN];
+  __shared__ __align__(16) PixMeta s_pm[2][kBwdBN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.y;
@@ -652,7 +666,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     const int64_t orow = o0 + row;
     // owner-side constants
     int code_o = 0, seg_o = -1;
-    PixMeta pm_o = {0.f, 0.f, 0.f, 0.f};
+    PixMeta pm_o = {0.f, 0.f, 0.f, 0.f};   // padding rows: all-zero weights
     if (row_ok) {
       if (!kProtoOwner) {
         code_o = a.rcode[orow];
@@ -692,18 +706,21 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
 
       float gv[32];
+      const bool tail = s0 + kBwdBN > s_hi;
+      const int own_rel = kProtoOwner ? (int)orow : seg_o - (int)s0 - cb;
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const int k = cb + q;
-        const bool valid = row_ok && (s0 + k < s_hi);
         const float z = __uint_as_float(v[q]);
+        float gq;
         if (!kProtoOwner) {
-          gv[q] = grad_elem(z, a.kappa_log2e, d.mode, code_o, s_code[acc][k],
-                            seg_o == (int)(s0 + k), pm_o, valid);
+          gq = grad_elem<kMode>(z, a.kappa_log2e, code_o, s_code[acc][k], q == own_rel, pm_o);
         } else {
-          gv[q] = grad_elem(z, a.kappa_log2e, d.mode, s_code[acc][k], code_o,
-                            s_seg[acc][k] == (int)orow, s_pm[acc][k], valid);
+          gq = grad_elem<kMode>(z, a.kappa_log2e, s_code[acc][k], code_o, s_seg[acc][k] == own_rel,
+                                s_pm[acc][k]);
         }
+        if (tail) gq = s0 + k < s_hi ? gq : 0.f;
+        gv[q] = row_ok ? gq : 0.f;
       }
       tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
       uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
@@ -861,10 +878,18 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
     set_error("segsort_fwd(tc): needs %zu bytes of shared memory", smem);
     return SPML_E_UNSUPPORTED;
   }
-  SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups);
-  segsort_fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+  if (d.mode == SPML_MODE_TAGS) {
+    SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel<SPML_MODE_TAGS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segsort_fwd_tc_kernel<SPML_MODE_TAGS>
+        <<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+  } else {
+    SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel<SPML_MODE_CLASS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segsort_fwd_tc_kernel<SPML_MODE_CLASS>
+        <<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+  }
   SPML_LAUNCH_CHECK("segsort_fwd_tc_kernel");
   return SPML_OK;
 }
@@ -874,6 +899,9 @@ int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
   const int64_t col_tiles = std::max<int64_t>(1, ceil_div(d.m, kBwdBM));
   const int64_t steps = std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kBwdBN));
   int64_t chunks = ceil_div(2 * 148, col_tiles * d.num_groups);
+  // with a column mask the buffer is capacity-sized and most column tiles are dead:
+  // keep enough row chunks for the live ones to fill the GPU
+  if (d.proto_valid) chunks = std::max<int64_t>(chunks, 16);
   return (int)std::max<int64_t>(1, std::min<int64_t>(chunks, steps));
 }
 
@@ -913,10 +941,18 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.out = demb;
     a.ld_out = ld_demb;
     a.beta = beta;
-    SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups, 1);
-    segsort_bwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(e128h, e128l, p64h, p64l, a);
+    if (d.mode == SPML_MODE_TAGS) {
+      SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<false, SPML_MODE_TAGS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      segsort_bwd_tc_kernel<false, SPML_MODE_TAGS>
+          <<<grid, kTcThreads, smem, st>>>(e128h, e128l, p64h, p64l, a);
+    } else {
+      SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<false, SPML_MODE_CLASS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      segsort_bwd_tc_kernel<false, SPML_MODE_CLASS>
+          <<<grid, kTcThreads, smem, st>>>(e128h, e128l, p64h, p64l, a);
+    }
     SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<emb>");
   }
   if (proto_partial) {
@@ -927,10 +963,18 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.out = proto_partial;
     a.ld_out = d.dim;
     a.beta = 0.f;
-    SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(d.m, kBwdBM), (unsigned)d.num_groups, (unsigned)chunks);
-    segsort_bwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(p128h, p128l, e64h, e64l, a);
+    if (d.mode == SPML_MODE_TAGS) {
+      SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true, SPML_MODE_TAGS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      segsort_bwd_tc_kernel<true, SPML_MODE_TAGS>
+          <<<grid, kTcThreads, smem, st>>>(p128h, p128l, e64h, e64l, a);
+    } else {
+      SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true, SPML_MODE_CLASS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      segsort_bwd_tc_kernel<true, SPML_MODE_CLASS>
+          <<<grid, kTcThreads, smem, st>>>(p128h, p128l, e64h, e64l, a);
+    }
     SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<proto>");
   }
   return SPML_OK;

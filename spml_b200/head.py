@@ -20,18 +20,20 @@ from . import model_utils, predictions, segsort_common
 
 
 def generate_clusters(embeddings, semantic_labels, instance_labels, local_features,
-                      label_divisor, semantic_ignore_index, num_clusters, iterations):
+                      label_divisor, semantic_ignore_index, num_clusters, iterations,
+                      batch_index_offset=None):
   """spml/models/embeddings/resnet_deeplab.py:90-148 (labels already at the embedding
   resolution).  The ignore id `labels.max() + 1` stays on the device."""
   if semantic_labels is not None and instance_labels is not None:
     labels = semantic_labels * label_divisor + instance_labels
     ignore_index = labels.max() + 1
-    labels = labels.masked_fill(semantic_labels == semantic_ignore_index, ignore_index)
+    # torch.where, not masked_fill: a tensor fill value would cost a device->host read-back
+    labels = torch.where(semantic_labels == semantic_ignore_index, ignore_index, labels)
   else:
     labels, ignore_index = None, None
   emb, emb_loc, lab, cid, bid = segsort_common.segment_by_kmeans(
       embeddings, labels, num_clusters, local_features=local_features,
-      ignore_index=ignore_index, iterations=iterations)
+      ignore_index=ignore_index, iterations=iterations, batch_index_offset=batch_index_offset)
   return {'cluster_embedding': emb, 'cluster_embedding_with_loc': emb_loc,
           'cluster_semantic_label': lab // label_divisor,
           'cluster_instance_label': lab % label_divisor,
@@ -56,7 +58,8 @@ class ContrastiveHead(nn.Module):
     datas = generate_clusters(
         embedding, semantic_label, instance_label, local_feature, cfg.network.label_divisor,
         cfg.dataset.semantic_ignore_index, cfg.network.kmeans_num_clusters,
-        cfg.network.kmeans_iterations)
+        cfg.network.kmeans_iterations,
+        batch_index_offset=0)   # rank-local image indices: `semantic_tag` is this rank's
     (protos, protos_loc, psem, pinst, pbid, cids) = (
         model_utils.gather_clustering_and_update_prototypes(
             [datas['cluster_embedding']], [datas['cluster_embedding_with_loc']],

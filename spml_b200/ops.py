@@ -120,9 +120,10 @@ class NormalizePack(torch.autograd.Function):
     el = torch.empty(cap, D + loc_ch, dtype=torch.float32, device=dev)
     nx = torch.empty(cap, dtype=torch.float32, device=dev)
     nc = torch.empty(cap, dtype=torch.float32, device=dev)
-    labels_out = torch.empty(cap, dtype=torch.int64, device=dev)
-    batch_out = torch.empty(cap, dtype=torch.int64, device=dev)
-    seed_out = torch.empty(cap, dtype=torch.int32, device=dev)
+    # rows past the live count are padding: integers read as 0 there (fixed-capacity mode)
+    labels_out = torch.zeros(cap, dtype=torch.int64, device=dev)
+    batch_out = torch.zeros(cap, dtype=torch.int64, device=dev)
+    seed_out = torch.zeros(cap, dtype=torch.int32, device=dev)
     call('spml_normalize_pack_fwd', ptr(emb), ptr(loc_c), loc_bs, loc_ch, ptr(labels),
          ptr(seeds_c), seed_bs, ptr(dst), B, D, n, int(batch_index_offset), EPS,
          ptr(e), ptr(el), ptr(nx), ptr(nc), ptr(labels_out), ptr(batch_out), ptr(seed_out),
@@ -184,7 +185,7 @@ def unique_inverse(lo, hi=None, bound=0, n_dev=None, want_keys=True):
   hi = _i64c(hi, 'unique(keys)').view(-1) if hi is not None else None
   n = lo.numel()
   dev = lo.device
-  inverse = torch.empty(n, dtype=torch.int64, device=dev)
+  inverse = (torch.zeros if n_dev is not None else torch.empty)(n, dtype=torch.int64, device=dev)
   uniq_hi = torch.empty(n, dtype=torch.int64, device=dev) if (want_keys and hi is not None) else None
   uniq_lo = torch.empty(n, dtype=torch.int64, device=dev) if want_keys else None
   count = torch.empty(1, dtype=torch.int32, device=dev)
@@ -204,7 +205,7 @@ class SegmentPrototypes(torch.autograd.Function):
   """calculate_prototypes_from_labels (spml/utils/segsort/common.py:11-41)."""
 
   @staticmethod
-  def forward(ctx, x, seg, m):
+  def forward(ctx, x, seg, m, rows_dev=None):
     x2 = _f32c(x, 'calculate_prototypes_from_labels(embeddings)').view(-1, x.shape[-1])
     seg = _i64c(seg, 'calculate_prototypes_from_labels(labels)').view(-1)
     if seg.numel() != x2.shape[0]:
@@ -216,9 +217,10 @@ class SegmentPrototypes(torch.autograd.Function):
     norms = torch.empty(m, dtype=torch.float32, device=x2.device)
     lib = _lib.load()
     ws = _workspace(lib.spml_segment_prototypes_workspace_bytes(m, dim), x2.device)
-    call('spml_segment_prototypes_fwd', ptr(x2), x2.shape[0], dim, ptr(seg), m, EPS,
-         ptr(protos), ptr(norms), ptr(ws), ws.numel(), stream_of(x2))
+    call('spml_segment_prototypes_fwd', ptr(x2), x2.shape[0], ptr(rows_dev), dim, ptr(seg), m,
+         EPS, ptr(protos), ptr(norms), ptr(ws), ws.numel(), stream_of(x2))
     ctx.save_for_backward(protos, norms, seg)
+    ctx.rows_dev = rows_dev
     ctx.xshape = x.shape
     return protos
 
@@ -227,10 +229,11 @@ class SegmentPrototypes(torch.autograd.Function):
     protos, norms, seg = ctx.saved_tensors
     dp = _f32c(dp, 'd(prototypes)')
     rows, dim = seg.numel(), protos.shape[1]
-    dx = torch.empty(rows, dim, dtype=torch.float32, device=protos.device)
-    call('spml_segment_prototypes_bwd', ptr(dp), ptr(protos), ptr(norms), ptr(seg), rows, dim,
-         protos.shape[0], EPS, 0.0, ptr(dx), stream_of(protos))
-    return dx.view(ctx.xshape), None, None
+    alloc = torch.zeros if ctx.rows_dev is not None else torch.empty
+    dx = alloc(rows, dim, dtype=torch.float32, device=protos.device)
+    call('spml_segment_prototypes_bwd', ptr(dp), ptr(protos), ptr(norms), ptr(seg), rows,
+         ptr(ctx.rows_dev), dim, protos.shape[0], EPS, 0.0, ptr(dx), stream_of(protos))
+    return dx.view(ctx.xshape), None, None, None
 
 
 # ------------------------------------------------------------------------------ C1 / C2
@@ -257,7 +260,7 @@ class SegsortProblem:
 
   def __init__(self, pix_code, seg, proto_code, kappa, mode, reduction=_lib.REDUCE_MEAN,
                row_index=None, group_off=None, col_off=None, num_groups=1, n_rows=None,
-               max_rows_per_group=None, proto_valid=None, path='auto'):
+               max_rows_per_group=None, proto_valid=None, path='auto', name=''):
     self.pix_code = _i64c(pix_code, 'segsort(pixel labels)').view(-1)
     self.seg = _i64c(seg, 'segsort(instance labels)').view(-1)
     self.proto_code = _i64c(proto_code, 'segsort(prototype labels)').view(-1)
@@ -268,6 +271,7 @@ class SegsortProblem:
     self.max_rows_per_group = (int(max_rows_per_group) if max_rows_per_group is not None
                                else self.n_rows)
     self.proto_valid = proto_valid
+    self.name = name      # label of this problem in bench.py's per-call profile
     # 'fp32' / 'tc' pin the CUDA-core / tcgen05 kernels (tests compare the two)
     self.path_bits = {'auto': 0, 'fp32': 1, 'tc': 2}[path]
     if proto_valid is not None and proto_valid.dtype != torch.uint8:
@@ -306,8 +310,10 @@ class SegsortLossFn(torch.autograd.Function):
     ws = _workspace(lib.spml_segsort_workspace_bytes(ctypes.byref(d)), dev)
     stats = torch.empty(max(problem.n_rows, 1), 3, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.PROFILE_TAG = ':' + problem.name if problem.name else ''
     call('spml_segsort_fwd', ctypes.byref(d), ptr(stats), None, ptr(loss), ptr(ws), ws.numel(),
          stream_of(emb))
+    _lib.PROFILE_TAG = ''
     ctx.save_for_backward(emb, protos, stats)
     ctx.problem = problem
     return loss
@@ -330,25 +336,44 @@ class SegsortLossFn(torch.autograd.Function):
     if need_e or need_p:
       lib = _lib.load()
       ws = _workspace(lib.spml_segsort_workspace_bytes(ctypes.byref(d)), dev)
+      _lib.PROFILE_TAG = ':' + problem.name if problem.name else ''
       call('spml_segsort_bwd', ctypes.byref(d), ptr(stats), ptr(grad_loss), 0.0, ptr(demb),
            emb.shape[1], ptr(dprotos), ptr(ws), ws.numel(), stream_of(emb))
+      _lib.PROFILE_TAG = ''
     return demb, dprotos, None
 
 
 # ------------------------------------------------------------------------------ C3
 
 
-def topk_ranking(q, qlab, p, plab, k):
+def topk_ranking(q, qlab, p, plab, k, qvalid=None, pvalid=None):
   q = _f32c(q, 'top_k_ranking(embeddings)')
   p = _f32c(p, 'top_k_ranking(prototypes)')
   q2, p2 = q.view(-1, q.shape[-1]), p.view(-1, p.shape[-1])
   qlab, plab = _i64c(qlab, 'top_k_ranking(labels)').view(-1), _i64c(plab, 'top_k_ranking').view(-1)
   nq = q2.shape[0]
-  labels = torch.empty(nq, k, dtype=torch.int64, device=q.device)
-  hits = torch.empty(1, dtype=torch.int32, device=q.device)
+  labels = torch.zeros(nq, k, dtype=torch.int64, device=q.device)
+  hits = torch.empty(2, dtype=torch.int32, device=q.device)
   call('spml_topk_ranking', ptr(q2), nq, ptr(p2), p2.shape[0], q2.shape[1], ptr(qlab),
-       ptr(plab), int(k), ptr(labels), None, ptr(hits), stream_of(q2))
-  acc = hits[0].to(torch.float32) / float(max(nq * k, 1))
-  if nq == 0:
-    acc = acc * float('nan')
+       ptr(plab), ptr(qvalid), ptr(pvalid), int(k), ptr(labels), None, ptr(hits), stream_of(q2))
+  # mean over (queries that took part) x k; 0 / 0 = nan like torch.mean of an empty tensor
+  acc = hits[0].to(torch.float32) / (hits[1].to(torch.float32) * float(k))
   return acc, labels
+
+
+def segment_labels(labels, batch, seg, rows_dev, divisor, num_classes, m_cap, dead_label,
+                   overflow):
+  """spml_segment_labels: per-pixel (sem, inst, keep) and per-segment (sem, inst, batch, live)
+  for fixed-capacity buffers.  Returns 7 tensors."""
+  cap, dev = labels.shape[0], labels.device
+  sem = torch.empty(cap, dtype=torch.int64, device=dev)
+  inst = torch.empty(cap, dtype=torch.int64, device=dev)
+  keep = torch.empty(cap, dtype=torch.int64, device=dev)
+  p_sem = torch.empty(m_cap, dtype=torch.int64, device=dev)
+  p_inst = torch.empty(m_cap, dtype=torch.int64, device=dev)
+  p_batch = torch.empty(m_cap, dtype=torch.int64, device=dev)
+  p_live = torch.empty(m_cap, dtype=torch.uint8, device=dev)
+  call('spml_segment_labels', ptr(labels), ptr(batch), ptr(seg), cap, ptr(rows_dev), int(divisor),
+       int(num_classes), int(m_cap), int(dead_label), ptr(sem), ptr(inst), ptr(keep), ptr(p_sem),
+       ptr(p_inst), ptr(p_batch), ptr(p_live), ptr(overflow), stream_of(labels))
+  return sem, inst, keep, p_sem, p_inst, p_batch, p_live

@@ -152,14 +152,12 @@ def _compress_seed_maps(cluster_indices, batch, n):
   return dense, per_image.to(torch.int32), int(per_image.max())
 
 
-def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indices=None,
-                      local_features=None, ignore_index=None, iterations=10):
-  """spml/utils/segsort/common.py:270-408 as ~20 asynchronous launches and ONE host
-  synchronisation (to size the returned tensors).
-
-  Returns (embeddings [N, C], embeddings_with_loc [N, C+L], labels [N],
-  cluster_indices [N], batch_indices [N]) exactly as the reference does.
-  """
+def segment_core(embeddings, labels, num_clusters, cluster_indices, local_features,
+                 ignore_index, iterations, batch_index_offset=None):
+  """Everything of segment_by_kmeans up to (not including) the host read-back.  Returns
+  fixed-CAPACITY tensors (batch * H * W rows; rows past the live count are padding) and
+  device-side counts: (e, el, labels, segment_ids, batch_ids, img_off int32 [B+1],
+  num_segments int32 [1])."""
   if embeddings.dim() != 4:
     raise ValueError('embeddings must be [batch, channels, height, width]')
   if not embeddings.is_cuda:
@@ -184,14 +182,33 @@ def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indi
   labels_c = ops._i64c(labels, 'segment_by_kmeans(labels)').view(B, n)
 
   dst, _, img_off = ops.valid_scan(labels_c, ignore_index, B, n)        # :355-365
-  batch_offset = B * (dev.index or 0)                                   # :376-377
+  if batch_index_offset is None:
+    batch_index_offset = B * (dev.index or 0)                           # :376-377
   e, el, lab, bid, seed = ops.NormalizePack.apply(
-      embeddings, local_features, labels_c, seeds, dst, batch_offset)
+      embeddings, local_features, labels_c, seeds, dst, batch_index_offset)
   _, km = ops.kmeans(el.detach(), img_off, B, n, num_k, iterations, seed, k_per_image)
   # :398-405: rank of (image, cluster, label) among the triples that occur
   inverse, _, _, count, _ = ops.unique_inverse(lab, hi=bid * num_k + km, bound=0,
                                                n_dev=img_off[B:], want_keys=False)
+  return e, el, lab, inverse, bid, img_off, count, batch_index_offset
+
+
+def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indices=None,
+                      local_features=None, ignore_index=None, iterations=10,
+                      batch_index_offset=None):
+  """spml/utils/segsort/common.py:270-408 as ~10 asynchronous launches and ONE host
+  synchronisation (to size the returned tensors).
+
+  Returns (embeddings [N, C], embeddings_with_loc [N, C+L], labels [N],
+  cluster_indices [N], batch_indices [N]) exactly as the reference does.
+  `batch_index_offset` (extra keyword, default = the reference's
+  `batch * device.index`) is the index given to the first image.
+  """
+  e, el, lab, inverse, bid, img_off, count, offset = segment_core(
+      embeddings, labels, num_clusters, cluster_indices, local_features, ignore_index,
+      iterations, batch_index_offset)
+  B = embeddings.shape[0]
   rows, segments = torch.stack([img_off[B], count[0]]).tolist()         # the one sync
   cid = inverse[:rows]
-  cid._spml_meta = SegmentMeta(segments, rows, img_off, B, batch_offset)
+  cid._spml_meta = SegmentMeta(segments, rows, img_off, B, offset)
   return e[:rows], el[:rows], lab[:rows], cid, bid[:rows]

@@ -208,7 +208,8 @@ def test_gather_generic_path_equals_fast_path():
 
 def test_abi_rejects_bad_arguments():
   lib = _lib.load()
-  rc = lib.spml_segment_prototypes_fwd(None, 10, 8, None, 4, 1e-12, None, None, None, 0, None)
+  rc = lib.spml_segment_prototypes_fwd(None, 10, None, 8, None, 4, 1e-12, None, None, None, 0,
+                                       None)
   assert rc == -1 and b'null' in lib.spml_last_error()
   x = torch.zeros(4, 200, device='cuda')
   with pytest.raises(RuntimeError, match='exceeds'):
