@@ -215,7 +215,10 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
       bar_t_empty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) int32_t s_ccode[2][kTcBN];
+  // prototype codes of the tiles in flight, written by warp 0.  The producer runs at most
+  // `stages` tiles ahead of the MMA and an MMA only starts once every epilogue warp is
+  // past the tile three before it, so a ring of stages + 3 <= 8 slots is never overrun.
+  __shared__ __align__(16) int32_t s_ccode[8][kTcBN];
   __shared__ float s_part[kTcBM][3];
   __shared__ float s_nll[kTcBM];
 
@@ -271,13 +274,20 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
         tc::tma_load_2d(&map_el, &bar_a_full, a_lo + (size_t)kb * kKBlockBytesA, kb * 64,
                         (int32_t)row0);
       }
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % a.stages, use = j / a.stages;
-        tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % a.stages, use = j / a.stages;
+      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
+      const int32_t c0 = c_begin + j * kTcBN;
+      // the tile's prototype codes ride along with the stage (ordered before lane 0's
+      // arrive by __syncwarp, seen by the epilogue through b_full -> MMA -> t_full)
+      for (int k = lane; k < kTcBN; k += 32)
+        s_ccode[j & 7][k] = c0 + k < c_end ? a.ccode[c0 + k] : 0;
+      __syncwarp();
+      if (lane == 0) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
         uint8_t* bh = b_ring + (size_t)s * stage_bytes;
         uint8_t* bl = bh + (size_t)a.nkb * kKBlockBytesB;
-        const int32_t c0 = c_begin + j * kTcBN;
         for (int kb = 0; kb < a.nkb; ++kb) {
           tc::tma_load_2d(&map_ph, &bar_b_full[s], bh + (size_t)kb * kKBlockBytesB, kb * 64, c0);
           tc::tma_load_2d(&map_pl, &bar_b_full[s], bl + (size_t)kb * kKBlockBytesB, kb * 64, c0);
@@ -321,7 +331,6 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     }
   } else {
     // ===================================================================== epilogue
-    const int et = tid - 64;                  // 0..255
     const int sp = warp & 3;                  // TMEM sub-partition of this warp
     const int half = (warp - 2) >> 2;         // which 64-column half of the tile
     const int row = sp * 32 + lane;
@@ -331,10 +340,8 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     float same = 0.f, diff = 0.f, self = 0.f;
 
     for (int j = 0; j < ntiles; ++j) {
-      const int acc = j & 1, ause = j >> 1;
+      const int acc = j & 1, ause = j >> 1, st = j & 7;
       const int c0 = c_begin + j * kTcBN;
-      if (et < kTcBN) s_ccode[acc][et] = c0 + et < c_end ? a.ccode[c0 + et] : 0;
-      tc::named_bar_sync(1, kTcEpiThreads);
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
       const bool tail = c0 + kTcBN > c_end;          // only the last tile has dead columns
@@ -350,7 +357,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
         }
-        const int4* codes = reinterpret_cast<const int4*>(&s_ccode[acc][cb]);
+        const int4* codes = reinterpret_cast<const int4*>(&s_ccode[st][cb]);
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const int4 c4 = codes[q4];
@@ -428,6 +435,7 @@ constexpr int kBwdBN = 64;
 constexpr int kBwdTileBytesA = kBwdBM * 128;   // one 64-wide K block of the owner tile
 constexpr int kBwdTileBytesB = kBwdBN * 128;   // one 64-wide block of the streamed tile
 constexpr int kBwdGBytes = kBwdBM * 128;       // G tile, 128 x 64 bf16
+constexpr int kBwdMaxStages = 4;
 
 struct TcBwdArgs {
   spml_segsort_desc d;        // for group ranges / reduction weights
@@ -490,12 +498,16 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
                       const __grid_constant__ CUtensorMap map_bh,
                       const __grid_constant__ CUtensorMap map_bl, const TcBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
-      bar_t_empty[2], bar_g_full[2], bar_g_empty[2], bar_d_full;
+  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[kBwdMaxStages],
+      bar_b_empty[kBwdMaxStages], bar_t_full[2], bar_t_empty[2], bar_g_full[2], bar_g_empty[2],
+      bar_d_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) int32_t s_code[2][kBwdBN];
-  __shared__ __align__(16) int32_t s_seg[2][kBwdBN];
-  __shared__ __align__(16) PixMeta s_pm[2][kBwdBN];
+  // metadata of the streamed tile in each ring stage, written by warp 0 before the stage's
+  // TMA is armed; a stage is only recycled after GEMM 2 of its tile, i.e. after the
+  // epilogue that reads these arrays
+  __shared__ __align__(16) int32_t s_code[kBwdMaxStages][kBwdBN];
+  __shared__ __align__(16) int32_t s_seg[kBwdMaxStages][kBwdBN];
+  __shared__ __align__(16) PixMeta s_pm[kBwdMaxStages][kBwdBN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.y;
@@ -549,9 +561,11 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
   if (warp == 0 && lane == 0) {
     tc::mbar_init(&bar_a_full, 1);
     tc::mbar_init(&bar_d_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kBwdMaxStages; ++s) {
       tc::mbar_init(&bar_b_full[s], 1);
       tc::mbar_init(&bar_b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bar_t_full[s], 1);
       tc::mbar_init(&bar_t_empty[s], kTcEpiThreads / 32);
       tc::mbar_init(&bar_g_full[s], kTcEpiThreads);
@@ -580,16 +594,33 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         tc::tma_load_2d(&map_al, &bar_a_full, a_lo + (size_t)kb * kBwdTileBytesA, kb * 64,
                         (int32_t)o0);
       }
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % a.stages, use = j / a.stages;
-        tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % a.stages, use = j / a.stages;
+      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
+      const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
+      for (int k = lane; k < kBwdBN; k += 32) {
+        const int64_t e = s0 + k;
+        const bool in = e < s_hi;
+        if (!kProtoOwner) {
+          s_code[s][k] = in ? a.ccode[e] : 0;
+        } else {
+          s_code[s][k] = in ? a.rcode[e] : 0;
+          s_seg[s][k] = in ? a.rseg[e] : -1;
+          PixMeta z = {0.f, 0.f, 0.f, 0.f};
+          s_pm[s][k] = in ? load_pix_meta(a, e, weight) : z;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
         uint8_t* bh = b_ring + (size_t)s * stage_bytes;
         uint8_t* bl = bh + (size_t)a.nkb * kBwdTileBytesB;
-        const int32_t s0 = (int32_t)(s_lo + (int64_t)j * kBwdBN);
         for (int kb = 0; kb < a.nkb; ++kb) {
-          tc::tma_load_2d(&map_bh, &bar_b_full[s], bh + (size_t)kb * kBwdTileBytesB, kb * 64, s0);
-          tc::tma_load_2d(&map_bl, &bar_b_full[s], bl + (size_t)kb * kBwdTileBytesB, kb * 64, s0);
+          tc::tma_load_2d(&map_bh, &bar_b_full[s], bh + (size_t)kb * kBwdTileBytesB, kb * 64,
+                          (int32_t)s0);
+          tc::tma_load_2d(&map_bl, &bar_b_full[s], bl + (size_t)kb * kBwdTileBytesB, kb * 64,
+                          (int32_t)s0);
         }
       }
     }
@@ -629,7 +660,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       tc::mbar_wait(&bar_a_full, 0);
       gemm1(0);
       for (int j = 0; j < ntiles; ++j) {
-        if (a.stages == 2 && j + 1 < ntiles) gemm1(j + 1);
+        if (a.stages >= 2 && j + 1 < ntiles) gemm1(j + 1);
         const int s = j % a.stages, gb = j & 1, guse = j >> 1;
         tc::mbar_wait(&bar_g_full[gb], guse & 1);
         tc::tcgen05_fence_after();
@@ -658,7 +689,6 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     }
   } else {
     // ===================================================================== epilogue
-    const int et = tid - 64;
     const int sp = warp & 3;
     const int half = (warp - 2) >> 2;          // 32-column half of the 64-wide S tile
     const int row = sp * 32 + lane;            // owner entity of this thread
@@ -680,21 +710,8 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     const uint32_t g_row_off = (row >> 3) * 1024 + sw * 128;
 
     for (int j = 0; j < ntiles; ++j) {
-      const int acc = j & 1, ause = j >> 1, gb = j & 1, guse = j >> 1;
+      const int acc = j & 1, ause = j >> 1, gb = j & 1, guse = j >> 1, st = j % a.stages;
       const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
-      if (et < kBwdBN) {
-        const int64_t e = s0 + et;
-        const bool in = e < s_hi;
-        if (!kProtoOwner) {
-          s_code[acc][et] = in ? a.ccode[e] : 0;
-        } else {
-          s_code[acc][et] = in ? a.rcode[e] : 0;
-          s_seg[acc][et] = in ? a.rseg[e] : -1;
-          PixMeta z = {0.f, 0.f, 0.f, 0.f};
-          s_pm[acc][et] = in ? load_pix_meta(a, e, weight) : z;
-        }
-      }
-      tc::named_bar_sync(1, kTcEpiThreads);
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
       uint32_t v[32];
@@ -714,10 +731,10 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         const float z = __uint_as_float(v[q]);
         float gq;
         if (!kProtoOwner) {
-          gq = grad_elem<kMode>(z, a.kappa_log2e, code_o, s_code[acc][k], q == own_rel, pm_o);
+          gq = grad_elem<kMode>(z, a.kappa_log2e, code_o, s_code[st][k], q == own_rel, pm_o);
         } else {
-          gq = grad_elem<kMode>(z, a.kappa_log2e, s_code[acc][k], code_o, s_seg[acc][k] == own_rel,
-                                s_pm[acc][k]);
+          gq = grad_elem<kMode>(z, a.kappa_log2e, s_code[st][k], code_o, s_seg[st][k] == own_rel,
+                                s_pm[st][k]);
         }
         if (tail) gq = s0 + k < s_hi ? gq : 0.f;
         gv[q] = row_ok ? gq : 0.f;
@@ -923,7 +940,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
   a.nkb = p.nkb;
   a.ksteps = p.ksteps;
-  a.stages = p.nkb <= 2 ? 2 : 1;
+  a.stages = p.nkb == 1 ? 4 : (p.nkb == 2 ? 2 : 1);   // what fits next to the A and G tiles
   a.n2 = (d.dim + 15) & ~15;
   a.tmem_cols = (2 * kBwdBN + a.n2) <= 256 ? 256 : 512;
   const size_t smem = 1024 + (size_t)2 * p.nkb * kBwdTileBytesA +
