@@ -298,6 +298,10 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kTcBM, kTcBN, 0, 0);
+      const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
+      const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
+      const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
+      const uint32_t ring_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), 16);
       tc::mbar_wait(&bar_a_full, 0);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % a.stages, use = j / a.stages;
@@ -306,23 +310,19 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
         tc::mbar_wait(&bar_b_full[s], use & 1);
         tc::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kTcBN;
-        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
-        const uint32_t bl = bh + a.nkb * kKBlockBytesB;
+        const uint32_t bh_lo = ring_lo + s * (stage_bytes >> 4);   // K-major: LBO unused (1)
+        const uint32_t bl_lo = bh_lo + a.nkb * (kKBlockBytesB >> 4);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < a.nkb; ++kb) {
           const int steps = min(4, a.ksteps - kb * 4);
-          const uint32_t ah_kb = tc::smem_u32(a_hi + (size_t)kb * kKBlockBytesA);
-          const uint32_t al_kb = tc::smem_u32(a_lo + (size_t)kb * kKBlockBytesA);
-          for (int ks = 0; ks < steps; ++ks) {
-            const uint32_t off = ks * 32;  // 16 bf16 inside the 128-byte swizzle atom
-            const uint64_t dah = tc::umma_desc_sw128(ah_kb + off, 16, 1024);
-            const uint64_t dal = tc::umma_desc_sw128(al_kb + off, 16, 1024);
-            const uint64_t dbh = tc::umma_desc_sw128(bh + kb * kKBlockBytesB + off, 16, 1024);
-            const uint64_t dbl = tc::umma_desc_sw128(bl + kb * kKBlockBytesB + off, 16, 1024);
-            tc::umma_bf16(d_tmem, dah, dbh, idesc, accumulate);
-            tc::umma_bf16(d_tmem, dal, dbh, idesc, 1);
-            tc::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+          uint32_t ah = ah_lo + kb * (kKBlockBytesA >> 4), al = al_lo + kb * (kKBlockBytesA >> 4);
+          uint32_t bh = bh_lo + kb * (kKBlockBytesB >> 4), bl = bl_lo + kb * (kKBlockBytesB >> 4);
+          for (int ks = 0; ks < steps; ++ks) {   // 16 bf16 = 32 bytes inside the swizzle atom
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bh, hi_k, idesc, accumulate);
+            tc::umma_bf16_words(d_tmem, al, hi_k, bh, hi_k, idesc, 1);
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bl, hi_k, idesc, 1);
             accumulate = 1;
+            ah += 2, al += 2, bh += 2, bl += 2;
           }
         }
         tc::umma_commit(&bar_b_empty[s]);    // the ring slot can be refilled
@@ -437,7 +437,19 @@ constexpr int kBwdTileBytesB = kBwdBN * 128;   // one 64-wide block of the strea
 constexpr int kBwdGBytes = kBwdBM * 128;       // G tile, 128 x 64 bf16
 constexpr int kBwdMaxStages = 4;
 
+#ifdef SPML_TC_TRACE
+#define SPML_TRACE(slot)                                                              \
+  do {                                                                                \
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && \
+        (threadIdx.x == 32 || threadIdx.x == 64))                                     \
+      a.trace[j * 16 + (slot)] = clock64();                                           \
+  } while (0)
+#else
+#define SPML_TRACE(slot) do { } while (0)
+#endif
+
 struct TcBwdArgs {
+  long long* trace;           // SPML_TC_TRACE builds: per-tile timestamps of CTA 0
   spml_segsort_desc d;        // for group ranges / reduction weights
   const int32_t* col_count;   // compact column count (proto_valid) or nullptr
   const int32_t* col_src;     // compact column -> original column, or nullptr
@@ -568,7 +580,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bar_t_full[s], 1);
       tc::mbar_init(&bar_t_empty[s], kTcEpiThreads / 32);
-      tc::mbar_init(&bar_g_full[s], kTcEpiThreads);
+      tc::mbar_init(&bar_g_full[s], kTcEpiThreads / 32);
       tc::mbar_init(&bar_g_empty[s], 1);
     }
     tc::fence_barrier_init();
@@ -629,60 +641,65 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     if (lane == 0) {
       constexpr uint32_t idesc1 = tc::umma_idesc_bf16(kBwdBM, kBwdBN, 0, 0);
       const uint32_t idesc2 = tc::umma_idesc_bf16(kBwdBM, a.n2, 0, 1);
+      const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
+      const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
+      const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
+      const uint32_t ring_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), 16);
+      // GEMM 2 operands: G tile K-major; streamed tile MN-major with LBO = next 64-wide N atom
+      const uint32_t g_lo = tc::umma_desc_lo(tc::smem_u32(g_ring), 16);
+      const uint32_t ring_mn_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), kBwdTileBytesB);
       auto gemm1 = [&](int j) {
         const int s = j % a.stages, use = j / a.stages;
         const int acc = j & 1, ause = j >> 1;
+        SPML_TRACE(8);
         tc::mbar_wait(&bar_t_empty[acc], (ause & 1) ^ 1);
+        SPML_TRACE(9);
         tc::mbar_wait(&bar_b_full[s], use & 1);
         tc::tcgen05_fence_after();
+        SPML_TRACE(10);
         const uint32_t d_tmem = tmem_base + acc * kBwdBN;
-        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
-        const uint32_t bl = bh + a.nkb * kBwdTileBytesB;
+        const uint32_t bh_lo = ring_lo + s * (stage_bytes >> 4);
+        const uint32_t bl_lo = bh_lo + a.nkb * (kBwdTileBytesB >> 4);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < a.nkb; ++kb) {
           const int steps = min(4, a.ksteps - kb * 4);
-          const uint32_t ah_kb = tc::smem_u32(a_hi + (size_t)kb * kBwdTileBytesA);
-          const uint32_t al_kb = tc::smem_u32(a_lo + (size_t)kb * kBwdTileBytesA);
+          uint32_t ah = ah_lo + kb * (kBwdTileBytesA >> 4), al = al_lo + kb * (kBwdTileBytesA >> 4);
+          uint32_t bh = bh_lo + kb * (kBwdTileBytesB >> 4), bl = bl_lo + kb * (kBwdTileBytesB >> 4);
           for (int ks = 0; ks < steps; ++ks) {
-            const uint32_t off = ks * 32;
-            const uint64_t dah = tc::umma_desc_sw128(ah_kb + off, 16, 1024);
-            const uint64_t dal = tc::umma_desc_sw128(al_kb + off, 16, 1024);
-            const uint64_t dbh = tc::umma_desc_sw128(bh + kb * kBwdTileBytesB + off, 16, 1024);
-            const uint64_t dbl = tc::umma_desc_sw128(bl + kb * kBwdTileBytesB + off, 16, 1024);
-            tc::umma_bf16(d_tmem, dah, dbh, idesc1, accumulate);
-            tc::umma_bf16(d_tmem, dal, dbh, idesc1, 1);
-            tc::umma_bf16(d_tmem, dah, dbl, idesc1, 1);
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bh, hi_k, idesc1, accumulate);
+            tc::umma_bf16_words(d_tmem, al, hi_k, bh, hi_k, idesc1, 1);
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bl, hi_k, idesc1, 1);
             accumulate = 1;
+            ah += 2, al += 2, bh += 2, bl += 2;
           }
         }
         tc::umma_commit(&bar_t_full[acc]);
+        SPML_TRACE(11);
       };
       tc::mbar_wait(&bar_a_full, 0);
       gemm1(0);
       for (int j = 0; j < ntiles; ++j) {
         if (a.stages >= 2 && j + 1 < ntiles) gemm1(j + 1);
         const int s = j % a.stages, gb = j & 1, guse = j >> 1;
+        SPML_TRACE(12);
         tc::mbar_wait(&bar_g_full[gb], guse & 1);
         tc::tcgen05_fence_after();
-        const uint32_t gh = tc::smem_u32(g_ring + (size_t)gb * 2 * kBwdGBytes);
-        const uint32_t gl = gh + kBwdGBytes;
-        const uint32_t bh = tc::smem_u32(b_ring + (size_t)s * stage_bytes);
-        const uint32_t bl = bh + a.nkb * kBwdTileBytesB;
+        SPML_TRACE(13);
+        uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
+        uint32_t bh = ring_mn_lo + s * (stage_bytes >> 4);
+        uint32_t bl = bh + a.nkb * (kBwdTileBytesB >> 4);
+        uint32_t accumulate = j > 0 ? 1u : 0u;
         for (int ks = 0; ks < kBwdBN / 16; ++ks) {
-          // A: G tile, K-major, 16 columns = 32 bytes inside the swizzle atom
-          const uint64_t dgh = tc::umma_desc_sw128(gh + ks * 32, 16, 1024);
-          const uint64_t dgl = tc::umma_desc_sw128(gl + ks * 32, 16, 1024);
-          // B: streamed tile, MN-major: 16 K rows = 2048 bytes; next 64-wide N atom = next
-          // K block of the stage (LBO)
-          const uint64_t dbh = tc::umma_desc_sw128(bh + ks * 2048, kBwdTileBytesB, 1024);
-          const uint64_t dbl = tc::umma_desc_sw128(bl + ks * 2048, kBwdTileBytesB, 1024);
-          const uint32_t accumulate = (j > 0 || ks > 0) ? 1u : 0u;
-          tc::umma_bf16(tmem_acc, dgh, dbh, idesc2, accumulate);
-          tc::umma_bf16(tmem_acc, dgl, dbh, idesc2, 1);
-          tc::umma_bf16(tmem_acc, dgh, dbl, idesc2, 1);
+          // A: 16 columns of G = 32 bytes inside the swizzle atom; B: 16 K rows = 2048 bytes
+          tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2, accumulate);
+          tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
+          tc::umma_bf16_words(tmem_acc, gh, hi_k, bl, hi_k, idesc2, 1);
+          accumulate = 1;
+          gh += 2, gl += 2, bh += 128, bl += 128;
         }
         tc::umma_commit(&bar_b_empty[s]);
         tc::umma_commit(&bar_g_empty[gb]);
+        SPML_TRACE(14);
         if (a.stages == 1 && j + 1 < ntiles) gemm1(j + 1);
       }
       tc::umma_commit(&bar_d_full);
@@ -712,8 +729,10 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     for (int j = 0; j < ntiles; ++j) {
       const int acc = j & 1, ause = j >> 1, gb = j & 1, guse = j >> 1, st = j % a.stages;
       const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
+      SPML_TRACE(0);
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
+      SPML_TRACE(1);
       uint32_t v[32];
       const int cb = half * 32;
       tc::tmem_ld_32x32(tmem_base + acc * kBwdBN + cb + (static_cast<uint32_t>(sp * 32) << 16), v);
@@ -739,7 +758,9 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         if (tail) gq = s0 + k < s_hi ? gq : 0.f;
         gv[q] = row_ok ? gq : 0.f;
       }
+      SPML_TRACE(2);
       tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
+      SPML_TRACE(3);
       uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
       uint8_t* gl = gh + kBwdGBytes;
 #pragma unroll
@@ -757,8 +778,11 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         *reinterpret_cast<uint4*>(gh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(gl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      tc::fence_proxy_async();
-      tc::mbar_arrive(&bar_g_full[gb]);
+      SPML_TRACE(4);
+      tc::fence_proxy_async();      // this thread's G stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_g_full[gb]);
+      SPML_TRACE(5);
     }
 
     // ---- d(owner) out of TMEM
@@ -912,6 +936,10 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
 }
 
 
+#ifdef SPML_TC_TRACE
+__device__ long long g_tc_trace[64 * 16];
+#endif
+
 int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
   const int64_t col_tiles = std::max<int64_t>(1, ceil_div(d.m, kBwdBM));
   const int64_t steps = std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kBwdBN));
@@ -958,6 +986,9 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.out = demb;
     a.ld_out = ld_demb;
     a.beta = beta;
+#ifdef SPML_TC_TRACE
+    SPML_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.trace), g_tc_trace));
+#endif
     dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups, 1);
     if (d.mode == SPML_MODE_TAGS) {
       SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<false, SPML_MODE_TAGS>,
@@ -980,6 +1011,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.out = proto_partial;
     a.ld_out = d.dim;
     a.beta = 0.f;
+    a.trace = nullptr;
     dim3 grid((unsigned)ceil_div(d.m, kBwdBM), (unsigned)d.num_groups, (unsigned)chunks);
     if (d.mode == SPML_MODE_TAGS) {
       SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true, SPML_MODE_TAGS>,
@@ -998,3 +1030,10 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
 }
 
 }  // namespace spml
+
+#ifdef SPML_TC_TRACE
+extern "C" int spml_debug_tc_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, spml::g_tc_trace, sizeof(long long) * 64 * 16) == cudaSuccess
+             ? 0 : -2;
+}
+#endif
