@@ -79,6 +79,7 @@ class StaticContrastiveHead(nn.Module):
     self.bank_mask = z(S, M, dtype=torch.int64)
     self.bank_live = z(S, M, dtype=torch.uint8)
     self.out = {}
+    self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
 
   # ------------------------------------------------------------------------------ one step
   def _forward(self):
@@ -111,31 +112,48 @@ class StaticContrastiveHead(nn.Module):
     else:
       p_all, psem_all, pmask_all, plive_all = protos, p_sem, cur_mask, p_live
 
-    # sem_ann (:184-201): labelled pixels x labelled live prototypes
-    _, rows, off = ops.valid_scan(keep.view(1, cap), 0, 1, cap, want_src=True)
-    problem = ops.SegsortProblem(
-        sem_pix, cid, psem_all, t.sem_ann_concentration, _lib.MODE_CLASS, row_index=rows,
-        group_off=off, num_groups=1, n_rows=cap, max_rows_per_group=cap,
-        proto_valid=plive_all & (psem_all < C).to(torch.uint8), name='sem_ann')
-    sem_ann = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_ann_loss_weight
-    # sem_occ: all live pixels x all live prototypes, image-tag masks
-    all_rows = torch.stack([img_off[0], img_off[B]])
-    problem = ops.SegsortProblem(
-        pix_mask, cid, pmask_all, t.sem_occ_concentration, _lib.MODE_TAGS, group_off=all_rows,
-        num_groups=1, n_rows=cap, max_rows_per_group=cap, proto_valid=plive_all, name='sem_occ')
-    sem_occ = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_occ_loss_weight
-    acc, _ = ops.topk_ranking(p_all.detach(), psem_all, p_all.detach(), psem_all, 5,
-                              qvalid=plive_all, pvalid=plive_all)           # :212-217
-    # img_sim (:220-240): rows grouped by image, each image sees its own prototypes
-    per_image = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-    per_image.scatter_add_(0, torch.where(p_live.bool(), p_bid + 1, torch.zeros_like(p_bid)),
-                           p_live.to(torch.int32))
-    col_off = torch.cumsum(per_image, 0, dtype=torch.int32)
-    problem = ops.SegsortProblem(
-        inst_pix, cid, p_inst, t.img_sim_concentration, _lib.MODE_CLASS,
-        reduction=_lib.REDUCE_GROUP_MEAN, group_off=img_off, col_off=col_off, num_groups=B,
-        n_rows=cap, max_rows_per_group=H * W, name='img_sim')
-    img_sim = ops.SegsortLossFn.apply(el, protos_loc, problem) * t.img_sim_loss_weight
+    # The three losses and the accuracy are independent: each runs on its own stream so
+    # that, inside the CUDA graph, they are parallel branches (at batch 1 a single loss only
+    # fills ~117 of 148 SMs for a few microseconds).  Autograd replays each backward on the
+    # stream of its forward, so the backward passes overlap too.
+    main = torch.cuda.current_stream(dev)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    streams = self._side_streams
+    for st in streams:
+      st.wait_event(fork)
+
+    with torch.cuda.stream(streams[0]):
+      # sem_ann (:184-201): labelled pixels x labelled live prototypes
+      _, rows, off = ops.valid_scan(keep.view(1, cap), 0, 1, cap, want_src=True)
+      problem = ops.SegsortProblem(
+          sem_pix, cid, psem_all, t.sem_ann_concentration, _lib.MODE_CLASS, row_index=rows,
+          group_off=off, num_groups=1, n_rows=cap, max_rows_per_group=cap,
+          proto_valid=plive_all & (psem_all < C).to(torch.uint8), name='sem_ann')
+      sem_ann = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_ann_loss_weight
+    with torch.cuda.stream(streams[1]):
+      # sem_occ: all live pixels x all live prototypes, image-tag masks
+      all_rows = torch.stack([img_off[0], img_off[B]])
+      problem = ops.SegsortProblem(
+          pix_mask, cid, pmask_all, t.sem_occ_concentration, _lib.MODE_TAGS, group_off=all_rows,
+          num_groups=1, n_rows=cap, max_rows_per_group=cap, proto_valid=plive_all, name='sem_occ')
+      sem_occ = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_occ_loss_weight
+    with torch.cuda.stream(streams[2]):
+      acc, _ = ops.topk_ranking(p_all.detach(), psem_all, p_all.detach(), psem_all, 5,
+                                qvalid=plive_all, pvalid=plive_all)           # :212-217
+    with torch.cuda.stream(streams[3]):
+      # img_sim (:220-240): rows grouped by image, each image sees its own prototypes
+      per_image = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+      per_image.scatter_add_(0, torch.where(p_live.bool(), p_bid + 1, torch.zeros_like(p_bid)),
+                             p_live.to(torch.int32))
+      col_off = torch.cumsum(per_image, 0, dtype=torch.int32)
+      problem = ops.SegsortProblem(
+          inst_pix, cid, p_inst, t.img_sim_concentration, _lib.MODE_CLASS,
+          reduction=_lib.REDUCE_GROUP_MEAN, group_off=img_off, col_off=col_off, num_groups=B,
+          n_rows=cap, max_rows_per_group=H * W, name='img_sim')
+      img_sim = ops.SegsortLossFn.apply(el, protos_loc, problem) * t.img_sim_loss_weight
+    for st in streams:
+      main.wait_stream(st)
 
     loss = sem_ann + sem_occ + img_sim                                       # train.py:213-219
     loss.backward()
