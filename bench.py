@@ -52,7 +52,8 @@ def parse_args():
   ap.add_argument('--workload', default='voc_scribble_b1', choices=sorted(synth.WORKLOADS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
-  ap.add_argument('--no-sweep', action='store_true')
+  ap.add_argument('--no-graph', action='store_true',
+                  help='launch the kernels directly instead of replaying the CUDA graph (for ncu)')
   return ap.parse_args()
 
 
@@ -235,13 +236,16 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
+    # keep stdout for the one JSON line: NCCL's version / debug lines go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     dist.init_process_group('nccl', device_id=dev)
   _lib.load()
 
   w = synth.WORKLOADS[args.workload]
   cfg = synth.make_config(w)
   # the product path: fixed-capacity head, forward + backward + bank update as one CUDA graph
-  head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels, device=dev)
+  head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels, device=dev,
+                               use_graph=not args.no_graph)
   dyn_head = ContrastiveHead(cfg).to(dev)     # reference-shaped drop-in API, timed for comparison
 
   # every rank gets its own minibatches (different seeds): weak scaling over images
@@ -313,6 +317,10 @@ def run_b200(args):
   step_resident(0)                       # builds the graph (untimed)
   torch.cuda.synchronize()
   kernels_per_step = head.kernels_per_step
+  if args.no_graph:
+    before = _lib.launch_count()
+    step_resident(1)
+    kernels_per_step = _lib.launch_count() - before
   ms_res, _, wall_res = timed(step_resident, args.steps, max(args.warmup, 3))
   ms_e2e, _, wall_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
   clocks = sampler.stop() if sampler else None
@@ -415,7 +423,7 @@ def run_b200(args):
                 'd2h_bytes_per_step': d2h_bytes},
         'gpu_launches': launches,
         'gpu_launches_per_step': kernels_per_step,
-        'cuda_graph': True,
+        'cuda_graph': not args.no_graph,
         'drop_in_api_ms_per_step': ms_dyn,
         'wall_s': {'resident': round(wall_res, 4), 'e2e': round(wall_e2e, 4)},
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,

@@ -236,7 +236,9 @@ typedef struct spml_segsort_desc {
   float kappa;
   int32_t mode;
   int32_t reduction;
-  int32_t reserved;
+  int32_t reserved;          /* bit 0: force the fp32 kernels, bit 1: force the tcgen05 kernels,
+                                bit 2 (bwd): the workspace is the one the forward call of
+                                this same problem used, its prepared operands are re-used */
 } spml_segsort_desc;
 
 size_t spml_segsort_workspace_bytes(const spml_segsort_desc* desc);

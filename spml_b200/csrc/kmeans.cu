@@ -2,9 +2,11 @@
 // (reference spml/utils/segsort/common.py:11-97).
 //
 // The whole clustering (T iterations, every image of the batch) is ONE persistent
-// cooperative launch: each CTA owns a fixed set of 128-pixel tiles, keeps its tile
-// resident in shared memory when it has only one, and the iterations are separated
-// by a grid-wide barrier instead of kernel boundaries.  An iteration is the
+// cooperative launch: each CTA owns a fixed set of 128-pixel tiles and keeps its tile
+// resident in shared memory when it has only one.  Iterations are not separated by
+// kernel boundaries or a grid barrier but by per-image flags: the CTA that finishes the
+// last tile of an image normalises that image's prototypes once and publishes them; the
+// CTAs of the image pick them up for the next E-step.  An iteration is the
 // reference's M-step (segment sums, L2-normalise) + E-step (argmax of x . P^T); the
 // E-step of iteration t is fused with the accumulation of the M-step of t + 1, so
 // the pixels are touched once per iteration.
@@ -20,6 +22,16 @@
 
 namespace spml {
 
+#ifdef SPML_KM_TRACE
+__device__ long long g_km_trace[16 * 8];
+#define KM_TRACE(slot)                                                        \
+  do {                                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) g_km_trace[it * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define KM_TRACE(slot) do { } while (0)
+#endif
+
 struct KmeansArgs {
   const float* x;            // [rows, dim]
   const int32_t* img_off;    // [batch + 1] or nullptr (one image of `rows_total` rows)
@@ -29,9 +41,11 @@ struct KmeansArgs {
   int num_clusters;          // stride of the per-image prototype arrays
   const int32_t* k_per_image;
   long long* sums;           // [iterations][batch][K][dim] fixed point, zeroed
+  float* protos;             // [iterations][batch][K][dim] unit prototypes (published per image)
+  unsigned* done;            // [iterations][batch] tiles that have accumulated, zeroed
+  unsigned* ready;           // [iterations][batch] prototypes published, zeroed
   const float* protos_in;    // A5: ready prototypes [K, dim] instead of sums
   int* poison;
-  unsigned* barrier;         // grid barrier counter, zeroed
   int iterations;
   const int32_t* labels_in;  // initial labels
   int32_t* labels_out;       // nullable
@@ -54,11 +68,11 @@ __device__ __forceinline__ bool tile_of(const KmeansArgs& p, int t, Tile& tile) 
   return tile.row0 < last;
 }
 
-// Bt[d][k] = unit prototype k0 + k of image b: from fixed-point sums (normalised here,
-// common.py:39) or from ready prototypes.  One warp per prototype, lanes across d; the
-// eight prototypes of a warp are fetched before the first reduction.
-__device__ __forceinline__ void stage_prototypes(const KmeansArgs& p, const long long* sums_b,
-                                                 int k0, int kc, float* Bt) {
+// Bt[d][k] = unit prototype k0 + k (k < 64) from a [K, dim] array of ready prototypes.
+// One warp per prototype, lanes across d; the eight prototypes of a warp are fetched
+// before anything is stored.
+__device__ __forceinline__ void stage_prototypes(const float* __restrict__ protos, int dim,
+                                                 int dpad, int k0, int kc, float* Bt) {
   constexpr int kWarps = kGemmThreads / 32;
   constexpr int kCols = BN / kWarps;            // 8 prototypes per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,38 +80,72 @@ __device__ __forceinline__ void stage_prototypes(const KmeansArgs& p, const long
 #pragma unroll
   for (int i = 0; i < kCols; ++i) {
     const int k = warp + i * kWarps;
-    const bool live = k < kc;
 #pragma unroll
     for (int s = 0; s < kMaxSlots; ++s) {
       const int d = lane + 32 * s;
-      float x = 0.f;
-      if (live && d < p.dim)
-        x = sums_b ? from_fixed(sums_b[(int64_t)(k0 + k) * p.dim + d])
-                   : p.protos_in[(int64_t)(k0 + k) * p.dim + d];
-      v[i][s] = x;
+      v[i][s] = (k < kc && d < dim) ? __ldcg(protos + (int64_t)(k0 + k) * dim + d) : 0.f;
     }
   }
 #pragma unroll
   for (int i = 0; i < kCols; ++i) {
     const int k = warp + i * kWarps;
-    float div = 1.f;
-    if (sums_b) {
-      float ss = 0.f;
-#pragma unroll
-      for (int s = 0; s < kMaxSlots; ++s) ss += v[i][s] * v[i][s];
-      const float nrm = sqrtf(warp_sum(ss));
-      div = nrm >= p.eps ? nrm : p.eps;
-    }
 #pragma unroll
     for (int s = 0; s < kMaxSlots; ++s) {
       const int d = lane + 32 * s;
-      if (d < p.dpad) Bt[d * LDB + k] = sums_b ? v[i][s] / div : v[i][s];
+      if (d < dpad) Bt[d * LDB + k] = v[i][s];
+    }
+  }
+}
+
+// value of a 2^-32 fixed-point sum with 32-bit conversions only
+__device__ __forceinline__ float fixed_to_float(long long s) {
+  const int hi = (int)(s >> 32);
+  const unsigned lo = (unsigned)(s & 0xffffffffll);
+  return fmaf((float)lo, 2.3283064365386963e-10f, (float)hi);
+}
+
+// The CTA that completed the last tile of image b turns the image's fixed-point sums into
+// unit prototypes (common.py:39: sum / max(||sum||, eps); an empty cluster is the zero
+// vector) and writes them to `out` [K, dim].  One warp per prototype, loads batched.
+__device__ __forceinline__ void finalize_prototypes(const KmeansArgs& p, const long long* sums_b,
+                                                    int kb, float* out) {
+  constexpr int kWarps = kGemmThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int kbase = 0; kbase < kb; kbase += 4 * kWarps) {
+    long long raw[4][kMaxSlots];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kbase + warp + i * kWarps;
+#pragma unroll
+      for (int s = 0; s < kMaxSlots; ++s) {
+        const int d = lane + 32 * s;
+        raw[i][s] = (k < kb && d < p.dim) ? __ldcg(sums_b + (int64_t)k * p.dim + d) : 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kbase + warp + i * kWarps;
+      float v[kMaxSlots], ss = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxSlots; ++s) {
+        v[s] = fixed_to_float(raw[i][s]);
+        ss += v[s] * v[s];
+      }
+      const float nrm = sqrtf(warp_sum(ss));
+      const float div = nrm >= p.eps ? nrm : p.eps;
+      if (k < kb) {
+#pragma unroll
+        for (int s = 0; s < kMaxSlots; ++s) {
+          const int d = lane + 32 * s;
+          if (d < p.dim) out[(int64_t)k * p.dim + d] = v[s] / div;
+        }
+      }
     }
   }
 }
 
 // E-step for the tile in At: s_lab[r] = argmax_k x_r . p_k, first index on ties.
-__device__ __forceinline__ void assign_tile(const KmeansArgs& p, const long long* sums_b, int kb,
+__device__ __forceinline__ void assign_tile(const KmeansArgs& p, const float* protos_b, int kb,
                                             const float* At, float* Bt, int* s_lab) {
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
   float best_v[TM];
@@ -107,7 +155,7 @@ __device__ __forceinline__ void assign_tile(const KmeansArgs& p, const long long
   for (int k0 = 0; k0 < kb; k0 += BN) {
     const int kc = min(BN, kb - k0);
     __syncthreads();  // the previous prototype tile is no longer read
-    stage_prototypes(p, sums_b, k0, kc, Bt);
+    stage_prototypes(protos_b, p.dim, p.dpad, k0, kc, Bt);
     __syncthreads();
     float acc[TM][TN];
     gemm_nt_tile(At, Bt, p.dpad, ty, tx, acc);
@@ -145,9 +193,11 @@ __device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile&
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = BM / (kGemmThreads / 32);
   const int r0 = warp * per, r1 = min(tile.rows, r0 + per);
-  long long run[kAccSlots];
+  // a value is round(x * 2^32) kept as hi * 2^16 + lo with two exact 32-bit integers
+  // (runs are at most 16 rows long, so neither half can overflow)
+  int run_hi[kAccSlots], run_lo[kAccSlots];
 #pragma unroll
-  for (int s = 0; s < kAccSlots; ++s) run[s] = 0;
+  for (int s = 0; s < kAccSlots; ++s) run_hi[s] = run_lo[s] = 0;
   int run_lab = -1;
   for (int r = r0; r < r1; ++r) {
     const int lab = s_lab[r];
@@ -156,9 +206,10 @@ __device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile&
 #pragma unroll
         for (int s = 0; s < kAccSlots; ++s) {
           const int d = lane + 32 * s;
-          if (d < p.dim && run[s] != 0)
-            atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d], run[s]);
-          run[s] = 0;
+          if (d < p.dim && (run_hi[s] | run_lo[s]) != 0)
+            atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d],
+                           (long long)run_hi[s] * 65536ll + run_lo[s]);
+          run_hi[s] = run_lo[s] = 0;
         }
       }
       run_lab = lab;
@@ -167,28 +218,25 @@ __device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile&
 #pragma unroll
     for (int s = 0; s < kAccSlots; ++s) {
       const int d = lane + 32 * s;
-      if (d < p.dim) run[s] += to_fixed(At[d * LDA + r], p.poison);
+      if (d < p.dim) {
+        const float v = At[d * LDA + r];
+        if (!(fabsf(v) <= 8.f)) *p.poison = 1;
+        const float scaled = v * 65536.f;
+        const float hi_f = rintf(scaled);
+        run_hi[s] += (int)hi_f;
+        run_lo[s] += (int)rintf((scaled - hi_f) * 65536.f);
+      }
     }
   }
   if (run_lab >= 0) {
 #pragma unroll
     for (int s = 0; s < kAccSlots; ++s) {
       const int d = lane + 32 * s;
-      if (d < p.dim && run[s] != 0) atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d], run[s]);
+      if (d < p.dim && (run_hi[s] | run_lo[s]) != 0)
+        atomic_add_i64(&sums_b[(int64_t)run_lab * p.dim + d],
+                       (long long)run_hi[s] * 65536ll + run_lo[s]);
     }
   }
-}
-
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
 }
 
 // Launched cooperatively (every CTA resident), grid <= number of tiles.
@@ -197,17 +245,20 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
   float* At = smem;                       // [dpad][LDA]
   float* Bt = At + (size_t)p.dpad * LDA;  // [dpad][LDB]
   __shared__ int s_lab[BM];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int total_tiles = p.batch * p.tiles_per_img;
   const bool resident = (int)gridDim.x >= total_tiles;   // one tile per CTA: load it once
-  const size_t per_iter = (size_t)p.batch * p.num_clusters * p.dim;
+  const size_t per_img = (size_t)p.num_clusters * p.dim;
+  const size_t per_iter = (size_t)p.batch * per_img;
 
   for (int it = 0; it <= p.iterations; ++it) {
+    KM_TRACE(0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       Tile tile;
       if (!tile_of(p, t, tile)) continue;
-      const int kb = p.k_per_image ? p.k_per_image[tile.b] : p.num_clusters;
-      const size_t img = (size_t)tile.b * p.num_clusters * p.dim;
+      const int b = tile.b;
+      const int kb = p.k_per_image ? p.k_per_image[b] : p.num_clusters;
       if (!resident || it == 0) {
         __syncthreads();
         load_rows_transposed<BM, LDA>(At, p.x, p.dim, nullptr, tile.row0, tile.rows, p.dim,
@@ -217,16 +268,46 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
         if (tid < tile.rows) s_lab[tid] = p.labels_in[tile.row0 + tid];
         __syncthreads();
       } else {
-        assign_tile(p, p.sums + (size_t)(it - 1) * per_iter + img, kb, At, Bt, s_lab);
+        // the prototypes of iteration it - 1 of THIS image (no grid-wide barrier)
+        if (tid == 0) {
+          volatile unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
+          while (*flag == 0) {
+          }
+          __threadfence();
+        }
+        __syncthreads();
+        KM_TRACE(1);
+        assign_tile(p, p.protos + (size_t)(it - 1) * per_iter + b * per_img, kb, At, Bt, s_lab);
+        KM_TRACE(2);
         if (it == p.iterations && tid < tile.rows) {
           if (p.labels_out) p.labels_out[tile.row0 + tid] = s_lab[tid];
           if (p.labels_out64) p.labels_out64[tile.row0 + tid] = s_lab[tid];
         }
       }
-      if (it < p.iterations)
-        accumulate_tile(p, tile, At, s_lab, p.sums + (size_t)it * per_iter + img);
+      if (it < p.iterations) {
+        long long* sums_b = p.sums + (size_t)it * per_iter + b * per_img;
+        accumulate_tile(p, tile, At, s_lab, sums_b);
+        KM_TRACE(3);
+        // publish: the CTA that adds the image's last tile normalises its prototypes
+        __syncthreads();
+        if (tid == 0) {
+          const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
+                                                     : p.rows_total);
+          const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
+          __threadfence();
+          s_last = atomicAdd(p.done + (size_t)it * p.batch + b, 1u) + 1 == tiles_b;
+        }
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          finalize_prototypes(p, sums_b, kb, p.protos + (size_t)it * per_iter + b * per_img);
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) atomicExch(p.ready + (size_t)it * p.batch + b, 1u);
+        }
+        KM_TRACE(4);
+      }
     }
-    if (it < p.iterations) grid_barrier(p.barrier, (unsigned)(it + 1) * gridDim.x);
   }
 }
 
@@ -239,7 +320,7 @@ __global__ void __launch_bounds__(kGemmThreads) nearest_prototype_kernel(KmeansA
   Tile tile;
   if (!tile_of(p, blockIdx.x, tile)) return;
   load_rows_transposed<BM, LDA>(At, p.x, p.dim, nullptr, tile.row0, tile.rows, p.dim, p.dpad);
-  assign_tile(p, nullptr, p.num_clusters, At, Bt, s_lab);
+  assign_tile(p, p.protos_in, p.num_clusters, At, Bt, s_lab);
   if (threadIdx.x < tile.rows) p.labels_out64[tile.row0 + threadIdx.x] = s_lab[threadIdx.x];
 }
 
@@ -258,9 +339,16 @@ static size_t kmeans_smem_bytes(int dpad) {
 
 extern "C" {
 
+// workspace: [poison | done, ready counters | fixed-point sums] (all zeroed) | unit prototypes
+static size_t kmeans_zeroed_bytes(int batch, int num_clusters, int dim, int iterations) {
+  return 16 + spml::align_up((size_t)2 * iterations * batch * sizeof(unsigned), 16) +
+         (size_t)iterations * batch * num_clusters * dim * sizeof(long long);
+}
+
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {
   if (batch <= 0 || num_clusters <= 0 || dim <= 0 || iterations <= 0) return 16;
-  return 16 + (size_t)iterations * batch * num_clusters * dim * sizeof(long long);
+  return kmeans_zeroed_bytes(batch, num_clusters, dim, iterations) +
+         (size_t)iterations * batch * num_clusters * dim * sizeof(float);
 }
 
 int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_per_image,
@@ -288,7 +376,8 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
     set_error("kmeans: workspace %zu < %zu bytes", workspace_bytes, need);
     return SPML_E_WORKSPACE;
   }
-  SPML_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations);
+  SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
 
   KmeansArgs p{};
   p.x = x;
@@ -299,9 +388,13 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.dpad = pad4(dim);
   p.num_clusters = num_clusters;
   p.k_per_image = k_per_image;
-  p.poison = reinterpret_cast<int*>(workspace);
-  p.barrier = reinterpret_cast<unsigned*>(workspace) + 1;
-  p.sums = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 16);
+  char* base = reinterpret_cast<char*>(workspace);
+  const size_t counters = align_up((size_t)2 * iterations * batch * sizeof(unsigned), 16);
+  p.poison = reinterpret_cast<int*>(base);
+  p.done = reinterpret_cast<unsigned*>(base + 16);
+  p.ready = p.done + (size_t)iterations * batch;
+  p.sums = reinterpret_cast<long long*>(base + 16 + counters);
+  p.protos = reinterpret_cast<float*>(base + zeroed);
   p.iterations = iterations;
   p.labels_in = init_labels;
   p.labels_out = labels_out;
@@ -355,3 +448,10 @@ int spml_nearest_prototype(const float* x, int64_t rows, int dim, const float* p
 }
 
 }  // extern "C"
+
+#ifdef SPML_KM_TRACE
+extern "C" int spml_debug_km_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, spml::g_km_trace, sizeof(long long) * 16 * 8) == cudaSuccess
+             ? 0 : -2;
+}
+#endif

@@ -159,16 +159,19 @@ constexpr int kMaxPerLane = (SPML_MAX_DIM + 31) / 32;  // channel slots per lane
 
 // d(emb) from d(e), d(el).  One warp per pixel for the dot products, then a
 // transposed, pixel-coalesced store.
+constexpr int kBwdTile = 32;            // pixels per CTA in the backward: 4 per warp
+constexpr int kBwdTileLd = kBwdTile + 1;
+
 __global__ void __launch_bounds__(kPackThreads)
 normalize_pack_bwd_kernel(const float* __restrict__ de, const float* __restrict__ del,
                           const float* __restrict__ e, const float* __restrict__ el,
                           const float* __restrict__ nx, const float* __restrict__ nc,
                           const int32_t* __restrict__ dst, int dim, int loc_ch, int n,
                           int tiles_per_img, float eps, float* __restrict__ demb) {
-  extern __shared__ float tile[];  // [dim][kTileLd]
+  extern __shared__ float tile[];  // [dim][kBwdTileLd]
   const int b = blockIdx.x / tiles_per_img;
-  const int p0 = (blockIdx.x % tiles_per_img) * kTile;
-  const int np = min(kTile, n - p0);
+  const int p0 = (blockIdx.x % tiles_per_img) * kBwdTile;
+  const int np = min(kBwdTile, n - p0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int dp = dim + loc_ch;
 
@@ -212,14 +215,14 @@ normalize_pack_bwd_kernel(const float* __restrict__ de, const float* __restrict_
 #pragma unroll
     for (int s = 0; s < kMaxPerLane; ++s) {
       const int d = lane + 32 * s;
-      if (d < dim) tile[d * kTileLd + px] = g[s];
+      if (d < dim) tile[d * kBwdTileLd + px] = g[s];
     }
   }
   __syncthreads();
-  const int px = tid % kTile;
+  const int px = tid % kBwdTile;
   if (px < np)
-    for (int d = tid / kTile; d < dim; d += kPackThreads / kTile)
-      demb[((int64_t)b * dim + d) * n + p0 + px] = tile[d * kTileLd + px];
+    for (int d = tid / kBwdTile; d < dim; d += kPackThreads / kBwdTile)
+      demb[((int64_t)b * dim + d) * n + p0 + px] = tile[d * kBwdTileLd + px];
 }
 
 static int tiles_per_image(int n) { return (int)ceil_div(n, kTile); }
@@ -293,10 +296,10 @@ int spml_normalize_pack_bwd(const float* de, const float* del, const float* e, c
   SPML_CHECK_SUPPORTED(loc_ch >= 0 && dim + loc_ch <= SPML_MAX_DIM,
                        "normalize_pack_bwd: dim %d + loc_ch %d exceeds %d", dim, loc_ch,
                        SPML_MAX_DIM);
-  const size_t smem = (size_t)dim * spml::kTileLd * sizeof(float);
+  const size_t smem = (size_t)dim * spml::kBwdTileLd * sizeof(float);
   SPML_CUDA(cudaFuncSetAttribute(spml::normalize_pack_bwd_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tpi = spml::tiles_per_image(n);
+  const int tpi = (int)spml::ceil_div(n, spml::kBwdTile);
   spml::normalize_pack_bwd_kernel<<<batch * tpi, spml::kPackThreads, smem,
                                     spml::as_stream(stream)>>>(
       de, del, e, el, nx, nc, dst, dim, loc_ch, n, tpi, eps, demb);

@@ -486,7 +486,8 @@ static int check_desc(const spml_segsort_desc* d, const char* who) {
 }
 
 // desc.reserved: bit 0 forces the fp32 CUDA-core path, bit 1 forces the tensor-core path
-// (tests compare the two); otherwise the tensor-core path runs whenever it supports the
+// (tests compare the two), bit 2 (backward only) says the workspace still holds the operands
+// prepared by the forward call of the same problem, so the pre-pass is skipped; otherwise the tensor-core path runs whenever it supports the
 // problem.  SPML_B200_SEGSORT=fp32|tc overrides the default.
 static bool use_tc_path(const spml_segsort_desc& d) {
   if (!segsort_tc_supported(d)) return false;
@@ -593,7 +594,8 @@ int spml_segsort_bwd(const spml_segsort_desc* d, const float* stats, const float
       partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + plan.bytes);
       SPML_CUDA(cudaMemsetAsync(partial, 0, partial_bytes, st));
     }
-    rc = segsort_bwd_tc(*d, plan, stats, grad_loss, beta, demb, ld_demb, partial, chunks, st);
+    rc = segsort_bwd_tc(*d, plan, stats, grad_loss, beta, demb, ld_demb, partial, chunks,
+                        (d->reserved & 4) != 0, st);
     if (rc != SPML_OK) return rc;
     if (dprotos) {
       const int64_t count = d->m * d->dim;

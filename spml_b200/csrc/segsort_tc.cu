@@ -952,8 +952,8 @@ int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
 
 int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
                    const float* grad_loss, float beta, float* demb, int64_t ld_demb,
-                   float* proto_partial, int chunks, cudaStream_t st) {
-  int rc = segsort_tc_prepare(d, p, st);
+                   float* proto_partial, int chunks, bool prepared, cudaStream_t st) {
+  int rc = prepared ? SPML_OK : segsort_tc_prepare(d, p, st);
   if (rc != SPML_OK) return rc;
   const uint64_t pitch = (uint64_t)p.dp * 2;
   TcBwdArgs a{};

@@ -45,6 +45,6 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
 int segsort_tc_proto_chunks(const spml_segsort_desc& d);
 int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
                    const float* grad_loss, float beta, float* demb, int64_t ld_demb,
-                   float* proto_partial, int chunks, cudaStream_t st);
+                   float* proto_partial, int chunks, bool prepared, cudaStream_t st);
 
 }  // namespace spml

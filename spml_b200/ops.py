@@ -316,6 +316,7 @@ class SegsortLossFn(torch.autograd.Function):
     _lib.PROFILE_TAG = ''
     ctx.save_for_backward(emb, protos, stats)
     ctx.problem = problem
+    ctx.workspace = ws          # the bf16 operands prepared by the forward are re-used
     return loss
 
   @staticmethod
@@ -334,8 +335,8 @@ class SegsortLossFn(torch.autograd.Function):
     if need_p:
       dprotos = torch.empty_like(protos)
     if need_e or need_p:
-      lib = _lib.load()
-      ws = _workspace(lib.spml_segsort_workspace_bytes(ctypes.byref(d)), dev)
+      ws = ctx.workspace
+      d.reserved |= 4
       _lib.PROFILE_TAG = ':' + problem.name if problem.name else ''
       call('spml_segsort_bwd', ctypes.byref(d), ptr(stats), ptr(grad_loss), 0.0, ptr(demb),
            emb.shape[1], ptr(dprotos), ptr(ws), ws.numel(), stream_of(emb))
