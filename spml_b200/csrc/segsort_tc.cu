@@ -17,6 +17,8 @@
 //               (one per 64-column half)
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -258,7 +260,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     tc::prefetch_tensormap(&map_ph);
     tc::prefetch_tensormap(&map_pl);
   }
-  if (warp == 1) tc::tmem_alloc(&s_tmem_base, 2 * kTcBN);
+  if (warp == 1) tc::tmem_alloc(&s_tmem_base, 4 * kTcBN);   // two accumulators of [hh+lh | hl]
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -286,11 +288,12 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
       __syncwarp();
       if (lane == 0) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
+        // per K block the hi tile is followed by the lo tile: read as ONE 256-row B operand
         uint8_t* bh = b_ring + (size_t)s * stage_bytes;
-        uint8_t* bl = bh + (size_t)a.nkb * kKBlockBytesB;
         for (int kb = 0; kb < a.nkb; ++kb) {
-          tc::tma_load_2d(&map_ph, &bar_b_full[s], bh + (size_t)kb * kKBlockBytesB, kb * 64, c0);
-          tc::tma_load_2d(&map_pl, &bar_b_full[s], bl + (size_t)kb * kKBlockBytesB, kb * 64, c0);
+          tc::tma_load_2d(&map_ph, &bar_b_full[s], bh + (size_t)(2 * kb) * kKBlockBytesB, kb * 64, c0);
+          tc::tma_load_2d(&map_pl, &bar_b_full[s], bh + (size_t)(2 * kb + 1) * kKBlockBytesB, kb * 64,
+                          c0);
         }
       }
     }
@@ -298,6 +301,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kTcBM, kTcBN, 0, 0);
+      constexpr uint32_t idesc2x = tc::umma_idesc_bf16(kTcBM, 2 * kTcBN, 0, 0);
       const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
       const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
       const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
@@ -309,20 +313,22 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
         tc::mbar_wait(&bar_t_empty[acc], (ause & 1) ^ 1);
         tc::mbar_wait(&bar_b_full[s], use & 1);
         tc::tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kTcBN;
-        const uint32_t bh_lo = ring_lo + s * (stage_bytes >> 4);   // K-major: LBO unused (1)
-        const uint32_t bl_lo = bh_lo + a.nkb * (kKBlockBytesB >> 4);
+        // MMAs cost ~150 cycles to issue whatever their N (scripts/micro/mma_issue.cu), so
+        // the three split products run as two instructions per K step:
+        //   A_hi x [B_hi ; B_lo]  (N = 256)  ->  columns [0,128) = hi.hi, [128,256) = hi.lo
+        //   A_lo x  B_hi          (N = 128)  ->  added to columns [0,128)
+        const uint32_t d_tmem = tmem_base + acc * 2 * kTcBN;
+        const uint32_t b_lo = ring_lo + s * (stage_bytes >> 4);   // K-major: LBO unused (1)
         uint32_t accumulate = 0;
         for (int kb = 0; kb < a.nkb; ++kb) {
           const int steps = min(4, a.ksteps - kb * 4);
           uint32_t ah = ah_lo + kb * (kKBlockBytesA >> 4), al = al_lo + kb * (kKBlockBytesA >> 4);
-          uint32_t bh = bh_lo + kb * (kKBlockBytesB >> 4), bl = bl_lo + kb * (kKBlockBytesB >> 4);
+          uint32_t bp = b_lo + kb * (2 * kKBlockBytesB >> 4);
           for (int ks = 0; ks < steps; ++ks) {   // 16 bf16 = 32 bytes inside the swizzle atom
-            tc::umma_bf16_words(d_tmem, ah, hi_k, bh, hi_k, idesc, accumulate);
-            tc::umma_bf16_words(d_tmem, al, hi_k, bh, hi_k, idesc, 1);
-            tc::umma_bf16_words(d_tmem, ah, hi_k, bl, hi_k, idesc, 1);
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bp, hi_k, idesc2x, accumulate);
+            tc::umma_bf16_words(d_tmem, al, hi_k, bp, hi_k, idesc, 1);
             accumulate = 1;
-            ah += 2, al += 2, bh += 2, bl += 2;
+            ah += 2, al += 2, bp += 2;
           }
         }
         tc::umma_commit(&bar_b_empty[s]);    // the ring slot can be refilled
@@ -349,8 +355,10 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
         const int cb = half * 64 + chunk * 32;
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_base + acc * kTcBN + cb + (static_cast<uint32_t>(sp * 32) << 16), v);
+        uint32_t v[32], w[32];
+        const uint32_t taddr = tmem_base + acc * 2 * kTcBN + cb + (static_cast<uint32_t>(sp * 32) << 16);
+        tc::tmem_ld_32x32(taddr, v);             // hi.hi + lo.hi
+        tc::tmem_ld_32x32(taddr + kTcBN, w);     // hi.lo
         tc::tmem_ld_wait();
         if (chunk == 1) {  // both loads of this warp are done: hand the accumulator back
           tc::tcgen05_fence_before();
@@ -365,7 +373,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int q = q4 * 4 + u;
-            float s = tc::fast_exp2(__uint_as_float(v[q]) * a.kappa_log2e);
+            float s = tc::fast_exp2((__uint_as_float(v[q]) + __uint_as_float(w[q])) * a.kappa_log2e);
             if (tail) s = c0 + cb + q < c_end ? s : 0.f;
             const bool match = kMode == SPML_MODE_TAGS ? (code_i & cc[u]) != 0 : code_i == cc[u];
             if (match) same += s; else diff += s;
@@ -412,7 +420,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tc::tmem_dealloc(tmem_base, 2 * kTcBN);
+    tc::tmem_dealloc(tmem_base, 4 * kTcBN);
   }
 }
 
@@ -436,6 +444,7 @@ constexpr int kBwdTileBytesA = kBwdBM * 128;   // one 64-wide K block of the own
 constexpr int kBwdTileBytesB = kBwdBN * 128;   // one 64-wide block of the streamed tile
 constexpr int kBwdGBytes = kBwdBM * 128;       // G tile, 128 x 64 bf16
 constexpr int kBwdMaxStages = 4;
+constexpr int kBwdGTmemCol = 384;   // TMEM columns [384, 512): two G buffers of (32 hi + 32 lo)
 
 #ifdef SPML_TC_TRACE
 #define SPML_TRACE(slot)                                                              \
@@ -465,6 +474,7 @@ struct TcBwdArgs {
   int nkb, ksteps, stages;
   int n2;                     // GEMM 2 N: dim rounded up to 16
   int tmem_cols;
+  int g_in_tmem;              // G tile handed to GEMM 2 through TMEM (TS MMA) instead of smem
 };
 
 // Per-pixel gradient weights.  G_ij = S_ij * w(match_ij, own_ij) with
@@ -685,17 +695,29 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         tc::mbar_wait(&bar_g_full[gb], guse & 1);
         tc::tcgen05_fence_after();
         SPML_TRACE(13);
-        uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
         uint32_t bh = ring_mn_lo + s * (stage_bytes >> 4);
         uint32_t bl = bh + a.nkb * (kBwdTileBytesB >> 4);
         uint32_t accumulate = j > 0 ? 1u : 0u;
-        for (int ks = 0; ks < kBwdBN / 16; ++ks) {
-          // A: 16 columns of G = 32 bytes inside the swizzle atom; B: 16 K rows = 2048 bytes
-          tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2, accumulate);
-          tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
-          tc::umma_bf16_words(tmem_acc, gh, hi_k, bl, hi_k, idesc2, 1);
-          accumulate = 1;
-          gh += 2, gl += 2, bh += 128, bl += 128;
+        if (a.g_in_tmem) {
+          // A = G straight from TMEM: 16 columns of G = 8 packed 32-bit TMEM columns
+          uint32_t gh = tmem_base + kBwdGTmemCol + gb * 64, gl = gh + 32;
+          for (int ks = 0; ks < kBwdBN / 16; ++ks) {
+            tc::umma_bf16_ts_words(tmem_acc, gh, bh, hi_k, idesc2, accumulate);
+            tc::umma_bf16_ts_words(tmem_acc, gl, bh, hi_k, idesc2, 1);
+            tc::umma_bf16_ts_words(tmem_acc, gh, bl, hi_k, idesc2, 1);
+            accumulate = 1;
+            gh += 8, gl += 8, bh += 128, bl += 128;
+          }
+        } else {
+          uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
+          for (int ks = 0; ks < kBwdBN / 16; ++ks) {
+            // A: 16 columns of G = 32 bytes inside the swizzle atom; B: 16 K rows = 2048 bytes
+            tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2, accumulate);
+            tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
+            tc::umma_bf16_words(tmem_acc, gh, hi_k, bl, hi_k, idesc2, 1);
+            accumulate = 1;
+            gh += 2, gl += 2, bh += 128, bl += 128;
+          }
         }
         tc::umma_commit(&bar_b_empty[s]);
         tc::umma_commit(&bar_g_empty[gb]);
@@ -761,25 +783,42 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       SPML_TRACE(2);
       tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
       SPML_TRACE(3);
-      uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
-      uint8_t* gl = gh + kBwdGBytes;
+      if (a.g_in_tmem) {
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int p2 = 0; p2 < 4; ++p2) {
-          const float x = gv[c4 * 8 + p2 * 2], y = gv[c4 * 8 + p2 * 2 + 1];
+        for (int c = 0; c < 16; ++c) {
+          const float x = gv[2 * c], y = gv[2 * c + 1];
           const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
-          hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
-          lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
+          hi[c] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
+          lo[c] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
         }
-        const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4);
-        const uint32_t off = g_row_off + ((chunk ^ sw) << 4);
-        *reinterpret_cast<uint4*>(gh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(gl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        const uint32_t taddr = tmem_base + kBwdGTmemCol + gb * 64 + (cb >> 1) +
+                               (static_cast<uint32_t>(sp * 32) << 16);
+        tc::tmem_st_32x16(taddr, hi);
+        tc::tmem_st_32x16(taddr + 32, lo);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+      } else {
+        uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
+        uint8_t* gl = gh + kBwdGBytes;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) {
+            const float x = gv[c4 * 8 + p2 * 2], y = gv[c4 * 8 + p2 * 2 + 1];
+            const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+            hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
+            lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
+          }
+          const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4);
+          const uint32_t off = g_row_off + ((chunk ^ sw) << 4);
+          *reinterpret_cast<uint4*>(gh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(gl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tc::fence_proxy_async();      // this thread's G stores -> visible to the tensor core
       }
       SPML_TRACE(4);
-      tc::fence_proxy_async();      // this thread's G stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_g_full[gb]);
       SPML_TRACE(5);
@@ -970,7 +1009,13 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.ksteps = p.ksteps;
   a.stages = p.nkb == 1 ? 4 : (p.nkb == 2 ? 2 : 1);   // what fits next to the A and G tiles
   a.n2 = (d.dim + 15) & ~15;
-  a.tmem_cols = (2 * kBwdBN + a.n2) <= 256 ? 256 : 512;
+  static int ts_mode = -1;
+  if (ts_mode < 0) {
+    const char* e = getenv("SPML_B200_G_TMEM");
+    ts_mode = e ? atoi(e) : 0;
+  }
+  a.g_in_tmem = ts_mode && (2 * kBwdBN + a.n2 <= kBwdGTmemCol);
+  a.tmem_cols = a.g_in_tmem ? 512 : ((2 * kBwdBN + a.n2) <= 256 ? 256 : 512);
   const size_t smem = 1024 + (size_t)2 * p.nkb * kBwdTileBytesA +
                       (size_t)a.stages * 2 * p.nkb * kBwdTileBytesB + (size_t)4 * kBwdGBytes;
   if (smem > 227 * 1024) {
