@@ -224,7 +224,8 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   __shared__ float s_part[kTcBM][3];
   __shared__ float s_nll[kTcBM];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role id
   const int g = blockIdx.y;
   const int64_t r_begin = a.group_off ? a.group_off[g] : 0;
   const int64_t r_end = a.group_off ? a.group_off[g + 1] : a.n_rows;
@@ -268,7 +269,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_a_full, 2u * a.nkb * kKBlockBytesA);
       for (int kb = 0; kb < a.nkb; ++kb) {
         tc::tma_load_2d(&map_eh, &bar_a_full, a_hi + (size_t)kb * kKBlockBytesA, kb * 64,
@@ -286,7 +287,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
       for (int k = lane; k < kTcBN; k += 32)
         s_ccode[j & 7][k] = c0 + k < c_end ? a.ccode[c0 + k] : 0;
       __syncwarp();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
         // per K block the hi tile is followed by the lo tile: read as ONE 256-row B operand
         uint8_t* bh = b_ring + (size_t)s * stage_bytes;
@@ -299,7 +300,9 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // the whole warp runs the loop (uniform control flow and operands); one elected lane
+    // issues the MMAs and commits
+    {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kTcBM, kTcBN, 0, 0);
       constexpr uint32_t idesc2x = tc::umma_idesc_bf16(kTcBM, 2 * kTcBN, 0, 0);
       const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
@@ -313,26 +316,29 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
         tc::mbar_wait(&bar_t_empty[acc], (ause & 1) ^ 1);
         tc::mbar_wait(&bar_b_full[s], use & 1);
         tc::tcgen05_fence_after();
-        // MMAs cost ~150 cycles to issue whatever their N (scripts/micro/mma_issue.cu), so
-        // the three split products run as two instructions per K step:
+        // the three split products run as two instructions per K step (an SS MMA with
+        // M = 128 costs max(~48, N/2) cycles, scripts/micro/mma_issue.cu):
         //   A_hi x [B_hi ; B_lo]  (N = 256)  ->  columns [0,128) = hi.hi, [128,256) = hi.lo
         //   A_lo x  B_hi          (N = 128)  ->  added to columns [0,128)
         const uint32_t d_tmem = tmem_base + acc * 2 * kTcBN;
         const uint32_t b_lo = ring_lo + s * (stage_bytes >> 4);   // K-major: LBO unused (1)
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          const int steps = min(4, a.ksteps - kb * 4);
-          uint32_t ah = ah_lo + kb * (kKBlockBytesA >> 4), al = al_lo + kb * (kKBlockBytesA >> 4);
-          uint32_t bp = b_lo + kb * (2 * kKBlockBytesB >> 4);
-          for (int ks = 0; ks < steps; ++ks) {   // 16 bf16 = 32 bytes inside the swizzle atom
-            tc::umma_bf16_words(d_tmem, ah, hi_k, bp, hi_k, idesc2x, accumulate);
-            tc::umma_bf16_words(d_tmem, al, hi_k, bp, hi_k, idesc, 1);
-            accumulate = 1;
-            ah += 2, al += 2, bp += 2;
+        if (tc::elect_one()) {
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            const int steps = min(4, a.ksteps - kb * 4);
+            uint32_t ah = ah_lo + kb * (kKBlockBytesA >> 4), al = al_lo + kb * (kKBlockBytesA >> 4);
+            uint32_t bp = b_lo + kb * (2 * kKBlockBytesB >> 4);
+            for (int ks = 0; ks < steps; ++ks) {   // 16 bf16 = 32 bytes inside the swizzle atom
+              tc::umma_bf16_words(d_tmem, ah, hi_k, bp, hi_k, idesc2x, accumulate);
+              tc::umma_bf16_words(d_tmem, al, hi_k, bp, hi_k, idesc, 1);
+              accumulate = 1;
+              ah += 2, al += 2, bp += 2;
+            }
           }
+          tc::umma_commit(&bar_b_empty[s]);    // the ring slot can be refilled
+          tc::umma_commit(&bar_t_full[acc]);   // the accumulator is complete
         }
-        tc::umma_commit(&bar_b_empty[s]);    // the ring slot can be refilled
-        tc::umma_commit(&bar_t_full[acc]);   // the accumulator is complete
+        __syncwarp();
       }
     }
   } else {
@@ -475,6 +481,7 @@ struct TcBwdArgs {
   int n2;                     // GEMM 2 N: dim rounded up to 16
   int tmem_cols;
   int g_in_tmem;              // G tile handed to GEMM 2 through TMEM (TS MMA) instead of smem
+  int stacked;                // nkb == 1: hi/lo streamed tiles read as one operand (2 MMAs per K step)
 };
 
 // Per-pixel gradient weights.  G_ij = S_ij * w(match_ij, own_ij) with
@@ -530,8 +537,10 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
   __shared__ __align__(16) int32_t s_code[kBwdMaxStages][kBwdBN];
   __shared__ __align__(16) int32_t s_seg[kBwdMaxStages][kBwdBN];
   __shared__ __align__(16) PixMeta s_pm[kBwdMaxStages][kBwdBN];
+  __shared__ int32_t s_segmin[kBwdMaxStages], s_segmax[kBwdMaxStages];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role id
   const int g = blockIdx.y;
   const spml_segsort_desc& d = a.d;
   const int64_t r_begin = d.group_off ? d.group_off[g] : 0;
@@ -604,11 +613,13 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  const uint32_t tmem_acc = tmem_base + 2 * kBwdBN;   // d(owner) accumulator columns
+  // stacked: an S buffer is [hi.hi + lo.hi | hi.lo] = 128 columns, d(owner) likewise
+  const uint32_t s_stride = a.stacked ? 2 * kBwdBN : kBwdBN;
+  const uint32_t tmem_acc = tmem_base + 2 * s_stride;   // d(owner) accumulator columns
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_a_full, 2u * a.nkb * kBwdTileBytesA);
       for (int kb = 0; kb < a.nkb; ++kb) {
         tc::tma_load_2d(&map_ah, &bar_a_full, a_hi + (size_t)kb * kBwdTileBytesA, kb * 64,
@@ -621,20 +632,28 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       const int s = j % a.stages, use = j / a.stages;
       tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
       const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
+      int seg_min = 0x7fffffff, seg_max = -1;
       for (int k = lane; k < kBwdBN; k += 32) {
         const int64_t e = s0 + k;
         const bool in = e < s_hi;
         if (!kProtoOwner) {
           s_code[s][k] = in ? a.ccode[e] : 0;
         } else {
+          const int sg = in ? a.rseg[e] : -1;
           s_code[s][k] = in ? a.rcode[e] : 0;
-          s_seg[s][k] = in ? a.rseg[e] : -1;
+          s_seg[s][k] = sg;
           PixMeta z = {0.f, 0.f, 0.f, 0.f};
           s_pm[s][k] = in ? load_pix_meta(a, e, weight) : z;
+          if (in) seg_min = min(seg_min, sg), seg_max = max(seg_max, sg);
         }
       }
+      if (kProtoOwner) {
+        seg_min = __reduce_min_sync(0xffffffffu, seg_min);
+        seg_max = __reduce_max_sync(0xffffffffu, seg_max);
+        if (lane == 0) s_segmin[s] = seg_min, s_segmax[s] = seg_max;
+      }
       __syncwarp();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
         uint8_t* bh = b_ring + (size_t)s * stage_bytes;
         uint8_t* bl = bh + (size_t)a.nkb * kBwdTileBytesB;
@@ -648,9 +667,13 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // the whole warp runs the loop (uniform control flow and operands); one elected lane
+    // issues the MMAs and commits
+    {
       constexpr uint32_t idesc1 = tc::umma_idesc_bf16(kBwdBM, kBwdBN, 0, 0);
+      constexpr uint32_t idesc1s = tc::umma_idesc_bf16(kBwdBM, 2 * kBwdBN, 0, 0);
       const uint32_t idesc2 = tc::umma_idesc_bf16(kBwdBM, a.n2, 0, 1);
+      const uint32_t idesc2s = tc::umma_idesc_bf16(kBwdBM, 64 + a.n2, 0, 1);
       const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
       const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
       const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
@@ -667,10 +690,23 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         tc::mbar_wait(&bar_b_full[s], use & 1);
         tc::tcgen05_fence_after();
         SPML_TRACE(10);
-        const uint32_t d_tmem = tmem_base + acc * kBwdBN;
+        const uint32_t d_tmem = tmem_base + acc * s_stride;
         const uint32_t bh_lo = ring_lo + s * (stage_bytes >> 4);
         const uint32_t bl_lo = bh_lo + a.nkb * (kBwdTileBytesB >> 4);
         uint32_t accumulate = 0;
+        if (tc::elect_one()) {
+        if (a.stacked) {
+          // the lo tile follows the hi tile: [B_hi ; B_lo] is one 128-row K-major operand:
+          // 2 MMAs (N = 128, 64) instead of 3 (N = 64) per K step; an SS MMA never costs
+          // less than ~48 cycles
+          uint32_t ah = ah_lo, al = al_lo, bp = bh_lo;
+          for (int ks = 0; ks < a.ksteps; ++ks) {
+            tc::umma_bf16_words(d_tmem, ah, hi_k, bp, hi_k, idesc1s, accumulate);   // hh | hl
+            tc::umma_bf16_words(d_tmem, al, hi_k, bp, hi_k, idesc1, 1);             // += lh
+            accumulate = 1;
+            ah += 2, al += 2, bp += 2;
+          }
+        } else
         for (int kb = 0; kb < a.nkb; ++kb) {
           const int steps = min(4, a.ksteps - kb * 4);
           uint32_t ah = ah_lo + kb * (kBwdTileBytesA >> 4), al = al_lo + kb * (kBwdTileBytesA >> 4);
@@ -684,6 +720,8 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
           }
         }
         tc::umma_commit(&bar_t_full[acc]);
+        }
+        __syncwarp();
         SPML_TRACE(11);
       };
       tc::mbar_wait(&bar_a_full, 0);
@@ -698,7 +736,28 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         uint32_t bh = ring_mn_lo + s * (stage_bytes >> 4);
         uint32_t bl = bh + a.nkb * (kBwdTileBytesB >> 4);
         uint32_t accumulate = j > 0 ? 1u : 0u;
-        if (a.g_in_tmem) {
+        if (tc::elect_one()) {
+        if (a.stacked) {
+          // MN-major B: the next 64-wide N atom (LBO) of the hi tile IS the lo tile, so
+          // G_hi x [P_hi | P_lo] is one MMA of N = 64 + n2; G_lo x P_hi adds to block 0
+          if (a.g_in_tmem) {
+            uint32_t gh = tmem_base + kBwdGTmemCol + gb * 64, gl = gh + 32;
+            for (int ks = 0; ks < kBwdBN / 16; ++ks) {
+              tc::umma_bf16_ts_words(tmem_acc, gh, bh, hi_k, idesc2s, accumulate);
+              tc::umma_bf16_ts_words(tmem_acc, gl, bh, hi_k, idesc2, 1);
+              accumulate = 1;
+              gh += 8, gl += 8, bh += 128;
+            }
+          } else {
+            uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
+            for (int ks = 0; ks < kBwdBN / 16; ++ks) {
+              tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2s, accumulate);
+              tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
+              accumulate = 1;
+              gh += 2, gl += 2, bh += 128;
+            }
+          }
+        } else if (a.g_in_tmem) {
           // A = G straight from TMEM: 16 columns of G = 8 packed 32-bit TMEM columns
           uint32_t gh = tmem_base + kBwdGTmemCol + gb * 64, gl = gh + 32;
           for (int ks = 0; ks < kBwdBN / 16; ++ks) {
@@ -721,10 +780,12 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         }
         tc::umma_commit(&bar_b_empty[s]);
         tc::umma_commit(&bar_g_empty[gb]);
+        if (j + 1 == ntiles) tc::umma_commit(&bar_d_full);
+        }
+        __syncwarp();
         SPML_TRACE(14);
         if (a.stages == 1 && j + 1 < ntiles) gemm1(j + 1);
       }
-      tc::umma_commit(&bar_d_full);
     }
   } else {
     // ===================================================================== epilogue
@@ -757,28 +818,78 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       SPML_TRACE(1);
       uint32_t v[32];
       const int cb = half * 32;
-      tc::tmem_ld_32x32(tmem_base + acc * kBwdBN + cb + (static_cast<uint32_t>(sp * 32) << 16), v);
-      tc::tmem_ld_wait();
+      const uint32_t s_addr = tmem_base + acc * s_stride + cb + (static_cast<uint32_t>(sp * 32) << 16);
+      tc::tmem_ld_32x32(s_addr, v);
+      if (a.stacked) {
+        uint32_t w[32];
+        tc::tmem_ld_32x32(s_addr + kBwdBN, w);   // the hi.lo block
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+      } else {
+        tc::tmem_ld_wait();
+      }
       tc::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
 
-      float gv[32];
-      const bool tail = s0 + kBwdBN > s_hi;
-      const int own_rel = kProtoOwner ? (int)orow : seg_o - (int)s0 - cb;
+      // G = exp(kappa S) * w(match, own), computed in place.  `own` (the pixel's own segment)
+      // holds for one column per pixel, so almost every (warp, tile) pair takes the lean loop
+      // that only applies the match weights: the epilogue is instruction-issue-bound (the
+      // tensor pipe needs ~900 cycles per step, this loop was ~2400 with the own selects in).
+      const float kl = a.kappa_log2e;
+      bool any_own;
+      int own_rel = 0;
+      if (!kProtoOwner) {
+        own_rel = seg_o - (int)s0 - cb;   // column of this pixel's own prototype
+        any_own = __any_sync(0xffffffffu, static_cast<unsigned>(own_rel) < 32u);
+      } else {
+        // pixels of the streamed tile own prototypes in [segmin, segmax] only
+        const int r_lo = (int)o0 + sp * 32;
+        any_own = s_segmax[st] >= r_lo && s_segmin[st] <= r_lo + 31;
+      }
+      if (!any_own) {
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int k = cb + q;
-        const float z = __uint_as_float(v[q]);
-        float gq;
-        if (!kProtoOwner) {
-          gq = grad_elem<kMode>(z, a.kappa_log2e, code_o, s_code[st][k], q == own_rel, pm_o);
-        } else {
-          gq = grad_elem<kMode>(z, a.kappa_log2e, s_code[st][k], code_o, s_seg[st][k] == own_rel,
-                                s_pm[st][k]);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const int4 cc = *reinterpret_cast<const int4*>(&s_code[st][cb + q4 * 4]);
+          const int c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int q = q4 * 4 + r;
+            const float e = tc::fast_exp2(__uint_as_float(v[q]) * kl);
+            const bool match = kMode == SPML_MODE_TAGS ? (code_o & c4[r]) != 0 : code_o == c4[r];
+            float w;
+            if (!kProtoOwner) {
+              w = match ? pm_o.w10 : pm_o.w00;
+            } else {
+              const float2 wq = *reinterpret_cast<const float2*>(&s_pm[st][cb + q]);   // w00, w10
+              w = match ? wq.y : wq.x;
+            }
+            v[q] = __float_as_uint(e * w);
+          }
         }
-        if (tail) gq = s0 + k < s_hi ? gq : 0.f;
-        gv[q] = row_ok ? gq : 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int k = cb + q;
+          const float z = __uint_as_float(v[q]);
+          float gq;
+          if (!kProtoOwner) {
+            gq = grad_elem<kMode>(z, kl, code_o, s_code[st][k], q == own_rel, pm_o);
+          } else {
+            gq = grad_elem<kMode>(z, kl, s_code[st][k], code_o, s_seg[st][k] == (int)orow,
+                                  s_pm[st][k]);
+          }
+          v[q] = __float_as_uint(gq);
+        }
+      }
+      if (kProtoOwner && !row_ok) {   // padding prototypes of the last owner tile
+#pragma unroll                        // (padding PIXEL rows have all-zero weights instead)
+        for (int q = 0; q < 32; ++q) v[q] = 0u;
+      }
+      if (s0 + kBwdBN > s_hi) {       // last streamed tile: columns past the end
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = s0 + cb + q < s_hi ? v[q] : 0u;
       }
       SPML_TRACE(2);
       tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
@@ -787,7 +898,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float x = gv[2 * c], y = gv[2 * c + 1];
+          const float x = __uint_as_float(v[2 * c]), y = __uint_as_float(v[2 * c + 1]);
           const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
           hi[c] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
           lo[c] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
@@ -806,7 +917,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p2 = 0; p2 < 4; ++p2) {
-            const float x = gv[c4 * 8 + p2 * 2], y = gv[c4 * 8 + p2 * 2 + 1];
+            const float x = __uint_as_float(v[c4 * 8 + p2 * 2]), y = __uint_as_float(v[c4 * 8 + p2 * 2 + 1]);
             const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
             hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
             lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
@@ -840,8 +951,17 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     const int nchunks = (a.n2 + 31) / 32;
     for (int ch = half; ch < nchunks; ch += 2) {
       uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_acc + ch * 32 + (static_cast<uint32_t>(sp * 32) << 16), v);
-      tc::tmem_ld_wait();
+      const uint32_t d_addr = tmem_acc + ch * 32 + (static_cast<uint32_t>(sp * 32) << 16);
+      tc::tmem_ld_32x32(d_addr, v);
+      if (a.stacked) {
+        uint32_t w[32];
+        tc::tmem_ld_32x32(d_addr + 64, w);       // G_hi x P_lo block
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+      } else {
+        tc::tmem_ld_wait();
+      }
       if (row_ok) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -1014,8 +1134,17 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     const char* e = getenv("SPML_B200_G_TMEM");
     ts_mode = e ? atoi(e) : 0;
   }
-  a.g_in_tmem = ts_mode && (2 * kBwdBN + a.n2 <= kBwdGTmemCol);
-  a.tmem_cols = a.g_in_tmem ? 512 : ((2 * kBwdBN + a.n2) <= 256 ? 256 : 512);
+  static int stack_mode = -1;
+  if (stack_mode < 0) {
+    const char* e = getenv("SPML_B200_STACK");
+    stack_mode = e ? atoi(e) : 1;
+  }
+  a.stacked = stack_mode && p.nkb == 1;
+  // TMEM columns: S buffers | d(owner) | (G buffers at kBwdGTmemCol)
+  const int s_cols = a.stacked ? 4 * kBwdBN : 2 * kBwdBN;
+  const int d_cols = a.stacked ? 64 + a.n2 : a.n2;
+  a.g_in_tmem = ts_mode && (s_cols + d_cols <= kBwdGTmemCol);
+  a.tmem_cols = a.g_in_tmem ? 512 : (s_cols + d_cols <= 256 ? 256 : 512);
   const size_t smem = 1024 + (size_t)2 * p.nkb * kBwdTileBytesA +
                       (size_t)a.stages * 2 * p.nkb * kBwdTileBytesB + (size_t)4 * kBwdGBytes;
   if (smem > 227 * 1024) {
@@ -1032,7 +1161,8 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.ld_out = ld_demb;
     a.beta = beta;
 #ifdef SPML_TC_TRACE
-    SPML_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.trace), g_tc_trace));
+    if (!getenv("SPML_B200_TRACE_PROTO"))
+      SPML_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.trace), g_tc_trace));
 #endif
     dim3 grid((unsigned)tc_tiles_x(d), (unsigned)d.num_groups, 1);
     if (d.mode == SPML_MODE_TAGS) {
@@ -1057,6 +1187,10 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     a.ld_out = d.dim;
     a.beta = 0.f;
     a.trace = nullptr;
+#ifdef SPML_TC_TRACE
+    if (getenv("SPML_B200_TRACE_PROTO"))
+      SPML_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.trace), g_tc_trace));
+#endif
     dim3 grid((unsigned)ceil_div(d.m, kBwdBM), (unsigned)d.num_groups, (unsigned)chunks);
     if (d.mode == SPML_MODE_TAGS) {
       SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true, SPML_MODE_TAGS>,

@@ -60,6 +60,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp.  tcgen05.mma / TMA / commit are uniform-datapath instructions:
+// issued under `if (lane == 0)` the compiler cannot prove their operands warp-uniform and wraps
+// every one in an ELECT / R2UR / BRA.U.ANY waterfall loop (~100-150 cycles per MMA measured,
+// scripts/micro/mma_issue.cu); inside a warp-uniform loop under elect.sync they issue at the
+// tensor-pipe floor (N/2 cycles for M = 128).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
