@@ -15,58 +15,26 @@
 // so the clustering is bit-reproducible whatever the tiling or scheduling.  The
 // consumer turns the sums into unit prototypes when it stages them.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
-#include "tile_gemm.cuh"
+#include "kmeans.cuh"
 
 namespace spml {
 
 #ifdef SPML_KM_TRACE
-__device__ long long g_km_trace[16 * 8];
+__device__ long long g_km_trace[16 * 16];
 #define KM_TRACE(slot)                                                        \
   do {                                                                        \
-    if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) g_km_trace[it * 8 + (slot)] = clock64(); \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) g_km_trace[it * 16 + (slot)] = clock64(); \
   } while (0)
 #else
 #define KM_TRACE(slot) do { } while (0)
 #endif
 
-struct KmeansArgs {
-  const float* x;            // [rows, dim]
-  const int32_t* img_off;    // [batch + 1] or nullptr (one image of `rows_total` rows)
-  int64_t rows_total;
-  int batch, tiles_per_img;
-  int dim, dpad;
-  int num_clusters;          // stride of the per-image prototype arrays
-  const int32_t* k_per_image;
-  long long* sums;           // [iterations][batch][K][dim] fixed point, zeroed
-  float* protos;             // [iterations][batch][K][dim] unit prototypes (published per image)
-  unsigned* done;            // [iterations][batch] tiles that have accumulated, zeroed
-  unsigned* ready;           // [iterations][batch] prototypes published, zeroed
-  const float* protos_in;    // A5: ready prototypes [K, dim] instead of sums
-  int* poison;
-  int iterations;
-  const int32_t* labels_in;  // initial labels
-  int32_t* labels_out;       // nullable
-  int64_t* labels_out64;     // nullable
-  float eps;
-};
 
-struct Tile {
-  int b;
-  int64_t row0;
-  int rows;
-};
-
-__device__ __forceinline__ bool tile_of(const KmeansArgs& p, int t, Tile& tile) {
-  tile.b = t / p.tiles_per_img;
-  const int64_t first = p.img_off ? p.img_off[tile.b] : 0;
-  const int64_t last = p.img_off ? p.img_off[tile.b + 1] : p.rows_total;
-  tile.row0 = first + (int64_t)(t % p.tiles_per_img) * BM;
-  tile.rows = (int)min((int64_t)BM, last - tile.row0);
-  return tile.row0 < last;
-}
 
 // Bt[d][k] = unit prototype k0 + k (k < 64) from a [K, dim] array of ready prototypes.
 // One warp per prototype, lanes across d; the eight prototypes of a warp are fetched
@@ -95,13 +63,6 @@ __device__ __forceinline__ void stage_prototypes(const float* __restrict__ proto
       if (d < dpad) Bt[d * LDB + k] = v[i][s];
     }
   }
-}
-
-// value of a 2^-32 fixed-point sum with 32-bit conversions only
-__device__ __forceinline__ float fixed_to_float(long long s) {
-  const int hi = (int)(s >> 32);
-  const unsigned lo = (unsigned)(s & 0xffffffffll);
-  return fmaf((float)lo, 2.3283064365386963e-10f, (float)hi);
 }
 
 // The CTA that completed the last tile of image b turns the image's fixed-point sums into
@@ -182,7 +143,6 @@ __device__ __forceinline__ void assign_tile(const KmeansArgs& p, const float* pr
   __syncthreads();
 }
 
-constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
 
 // M-step accumulation for the tile: each warp walks 16 consecutive rows with its lanes
 // across the channels and flushes a fixed-point run total whenever the label changes
@@ -221,10 +181,10 @@ __device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile&
       if (d < p.dim) {
         const float v = At[d * LDA + r];
         if (!(fabsf(v) <= 8.f)) *p.poison = 1;
-        const float scaled = v * 65536.f;
-        const float hi_f = rintf(scaled);
-        run_hi[s] += (int)hi_f;
-        run_lo[s] += (int)rintf((scaled - hi_f) * 65536.f);
+        int hi, lo;
+        split_fixed(v, hi, lo);
+        run_hi[s] += hi;
+        run_lo[s] += lo;
       }
     }
   }
@@ -340,15 +300,33 @@ static size_t kmeans_smem_bytes(int dpad) {
 extern "C" {
 
 // workspace: [poison | done, ready counters | fixed-point sums] (all zeroed) | unit prototypes
-static size_t kmeans_zeroed_bytes(int batch, int num_clusters, int dim, int iterations) {
+static size_t kmeans_zeroed_bytes(int batch, int num_clusters, int dim, int iterations,
+                                  int replicas) {
   return 16 + spml::align_up((size_t)2 * iterations * batch * sizeof(unsigned), 16) +
-         (size_t)iterations * batch * num_clusters * dim * sizeof(long long);
+         (size_t)iterations * replicas * batch * num_clusters * dim * sizeof(long long);
+}
+
+// offset of the split (bf16) prototypes of the tensor-core path: behind the zeroed block (sized
+// for its replicated sums) and the fp32 prototypes
+static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iterations) {
+  return spml::align_up(
+      kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, spml::kKmReplicas) +
+          (size_t)iterations * batch * num_clusters * dim * sizeof(float),
+      256);
+}
+
+// The E-step runs on the tensor cores whenever the shape is supported;
+// SPML_B200_KMEANS=fp32|tc overrides (read per call so that tests can compare the two).
+static bool kmeans_use_tc(int dim) {
+  if (!spml::kmeans_tc_supported(dim)) return false;
+  const char* e = getenv("SPML_B200_KMEANS");
+  return !(e && !strcmp(e, "fp32"));
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {
   if (batch <= 0 || num_clusters <= 0 || dim <= 0 || iterations <= 0) return 16;
-  return kmeans_zeroed_bytes(batch, num_clusters, dim, iterations) +
-         (size_t)iterations * batch * num_clusters * dim * sizeof(float);
+  return kmeans_split_offset(batch, num_clusters, dim, iterations) +
+         spml::kmeans_tc_split_bytes(batch, num_clusters, dim, iterations);
 }
 
 int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_per_image,
@@ -376,7 +354,9 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
     set_error("kmeans: workspace %zu < %zu bytes", workspace_bytes, need);
     return SPML_E_WORKSPACE;
   }
-  const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations);
+  const bool use_tc = kmeans_use_tc(dim);
+  const int replicas = use_tc ? kKmReplicas : 1;
+  const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, replicas);
   SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
 
   KmeansArgs p{};
@@ -394,6 +374,7 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.done = reinterpret_cast<unsigned*>(base + 16);
   p.ready = p.done + (size_t)iterations * batch;
   p.sums = reinterpret_cast<long long*>(base + 16 + counters);
+  p.replicas = replicas;
   p.protos = reinterpret_cast<float*>(base + zeroed);
   p.iterations = iterations;
   p.labels_in = init_labels;
@@ -401,12 +382,15 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.labels_out64 = labels_out_i64;
   p.eps = 1e-12f;
 
-  const size_t smem = kmeans_smem_bytes(p.dpad);
-  SPML_CUDA(cudaFuncSetAttribute(kmeans_persistent_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int device = 0, sms = 0, per_sm = 0;
   SPML_CUDA(cudaGetDevice(&device));
   SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (use_tc)
+    return kmeans_tc_launch(p, base + kmeans_split_offset(batch, num_clusters, dim, iterations),
+                            sms, st);
+  const size_t smem = kmeans_smem_bytes(p.dpad);
+  SPML_CUDA(cudaFuncSetAttribute(kmeans_persistent_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SPML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_persistent_kernel,
                                                           kGemmThreads, smem));
   SPML_CHECK_SUPPORTED(per_sm >= 1, "kmeans: kernel does not fit on an SM (dim %d)", dim);
@@ -451,7 +435,7 @@ int spml_nearest_prototype(const float* x, int64_t rows, int dim, const float* p
 
 #ifdef SPML_KM_TRACE
 extern "C" int spml_debug_km_trace(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, spml::g_km_trace, sizeof(long long) * 16 * 8) == cudaSuccess
+  return cudaMemcpyFromSymbol(host_out, spml::g_km_trace, sizeof(long long) * 16 * 16) == cudaSuccess
              ? 0 : -2;
 }
 #endif

@@ -1,41 +1,70 @@
 // C3: top_k_ranking (reference spml/utils/segsort/eval.py:9-52) without the full
-// [Q, M] argsort: each warp owns one query row, streams the prototype bank through
+// [Q, M] argsort: each warp owns one query row, streams prototype tiles through
 // shared memory, keeps a sorted top-k list per lane in registers and merges the 32
 // lists with k rounds of a warp arg-max.  Order: similarity descending, lowest
 // prototype index first on ties.
+//
+// The prototype bank is split over a thread-block CLUSTER of 8 CTAs (CTA r takes the
+// column tiles r, r + 8, ...): the problem is small (M^2 D flops) and latency-bound per
+// tile, so the tiles of one query block run on 8 SMs at once.  Each CTA leaves its
+// per-query top-k in its own shared memory; CTA 0 of the cluster merges the 8 lists
+// through distributed shared memory.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace spml {
 
 constexpr int kTopkWarps = 8;
 constexpr int kTopkCols = 64;  // prototypes staged per step
+constexpr int kTopkCluster = 8;  // CTAs sharing one block of queries
 
-template <int KMAX>
-__global__ void __launch_bounds__(kTopkWarps * 32)
+template <int KMAX, int QW>
+__global__ void __launch_bounds__(kTopkWarps * 32, QW > 1 ? 2 : 1)
 topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p, int64_t m,
             int dim, const int64_t* __restrict__ qlab, const int64_t* __restrict__ plab,
             const uint8_t* __restrict__ qvalid, const uint8_t* __restrict__ pvalid, int k,
             int64_t* __restrict__ topk_labels, int64_t* __restrict__ topk_index,
             int32_t* hit_count) {
-  extern __shared__ float smem[];
-  const int ldq = dim, ldp = dim + 1;
-  float* Qs = smem;                          // [warps][dim]
-  float* Ps = Qs + kTopkWarps * ldq;         // [kTopkCols][dim + 1]
+  // A warp owns QW query rows: a prototype value read from shared memory feeds QW FMAs
+  // (the kernel is bound by shared-memory reads, not by the FMAs).
+  constexpr int kQ = kTopkWarps * QW;        // queries per CTA (and per cluster)
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float s_val[kQ][KMAX];          // this CTA's top-k per query, read by cluster rank 0
+  __shared__ int s_idx[kQ][KMAX];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int ldq = (dim + 3) & ~3, ldp = dim + 1;
+  float* Qs = smem;                          // [kQ][ldq], zero padded to a multiple of 4
+  float* Ps = Qs + kQ * ldq;                 // [kTopkCols][dim + 1]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * kTopkWarps + warp;
-  const bool active = row < nq && (!qvalid || qvalid[row]);
-  if (!__syncthreads_or(active)) return;     // fixed-capacity buffers: a block of padding rows
-
-  for (int d = lane; d < dim; d += 32) Qs[warp * ldq + d] = active ? q[row * dim + d] : 0.f;
-
-  float lv[KMAX];
-  int li[KMAX];
+  const int64_t row0 = (int64_t)(blockIdx.x / kTopkCluster) * kQ + warp * QW;
+  bool active[QW];
+  bool any = false;
 #pragma unroll
-  for (int s = 0; s < KMAX; ++s) lv[s] = -INFINITY, li[s] = 0x7fffffff;
+  for (int i = 0; i < QW; ++i) {
+    active[i] = row0 + i < nq && (!qvalid || qvalid[row0 + i]);
+    any |= active[i];
+  }
+  // fixed-capacity buffers: a block of padding rows (the same for the whole cluster)
+  if (!__syncthreads_or(any)) return;
 
-  for (int64_t c0 = 0; c0 < m; c0 += kTopkCols) {
+#pragma unroll
+  for (int i = 0; i < QW; ++i)
+    for (int d = lane; d < ldq; d += 32)
+      Qs[(warp * QW + i) * ldq + d] = (active[i] && d < dim) ? q[(row0 + i) * dim + d] : 0.f;
+
+  float lv[QW][KMAX];
+  int li[QW][KMAX];
+#pragma unroll
+  for (int i = 0; i < QW; ++i)
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) lv[i][s] = -INFINITY, li[i][s] = 0x7fffffff;
+
+  for (int64_t c0 = (int64_t)rank * kTopkCols; c0 < m; c0 += kTopkCluster * kTopkCols) {
     const int cc = (int)min((int64_t)kTopkCols, m - c0);
     if (pvalid) {   // skip tiles made of dead columns only (block-uniform)
       const bool live = threadIdx.x < cc && pvalid[c0 + threadIdx.x];
@@ -46,58 +75,128 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
       for (int d = lane; d < dim; d += 32)
         Ps[j * ldp + d] = j < cc ? p[(c0 + j) * dim + d] : 0.f;
     __syncthreads();
-    float a0 = 0.f, a1 = 0.f;
-    for (int d = 0; d < dim; ++d) {
-      const float qv = Qs[warp * ldq + d];
-      a0 = fmaf(qv, Ps[lane * ldp + d], a0);
-      a1 = fmaf(qv, Ps[(lane + 32) * ldp + d], a1);
+    float acc[QW][2];
+#pragma unroll
+    for (int i = 0; i < QW; ++i) acc[i][0] = acc[i][1] = 0.f;
+    const float* p0 = Ps + lane * ldp;
+    const float* p1 = Ps + (lane + 32) * ldp;
+    const float* qw = Qs + warp * QW * ldq;
+    int d = 0;
+    for (; d + 4 <= dim; d += 4) {   // d ascending: the same fmaf chain per (query, column) as ever
+      const float b0[4] = {p0[d], p0[d + 1], p0[d + 2], p0[d + 3]};
+      const float b1[4] = {p1[d], p1[d + 1], p1[d + 2], p1[d + 3]};
+#pragma unroll
+      for (int i = 0; i < QW; ++i) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qw + i * ldq + d);
+        const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[i][0] = fmaf(qa[u], b0[u], acc[i][0]);
+          acc[i][1] = fmaf(qa[u], b1[u], acc[i][1]);
+        }
+      }
+    }
+    for (; d < dim; ++d) {
+#pragma unroll
+      for (int i = 0; i < QW; ++i) {
+        const float qv = qw[i * ldq + d];
+        acc[i][0] = fmaf(qv, p0[d], acc[i][0]);
+        acc[i][1] = fmaf(qv, p1[d], acc[i][1]);
+      }
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = lane + 32 * h;
-      const float v = h ? a1 : a0;
-      if (j < cc && (!pvalid || pvalid[c0 + j]) && v > lv[KMAX - 1]) {
-        // columns arrive in increasing index, so a strict '>' keeps the lowest index on ties
-        lv[KMAX - 1] = v;
-        li[KMAX - 1] = (int)(c0 + j);
+      const bool col_ok = j < cc && (!pvalid || pvalid[c0 + j]);
 #pragma unroll
-        for (int s = KMAX - 1; s > 0; --s) {
-          if (lv[s] > lv[s - 1]) {
-            const float tv = lv[s]; lv[s] = lv[s - 1]; lv[s - 1] = tv;
-            const int ti = li[s]; li[s] = li[s - 1]; li[s - 1] = ti;
+      for (int i = 0; i < QW; ++i) {
+        const float v = acc[i][h];
+        if (col_ok && v > lv[i][KMAX - 1]) {
+          // columns arrive in increasing index, so a strict '>' keeps the lowest index on ties
+          lv[i][KMAX - 1] = v;
+          li[i][KMAX - 1] = (int)(c0 + j);
+#pragma unroll
+          for (int s = KMAX - 1; s > 0; --s) {
+            if (lv[i][s] > lv[i][s - 1]) {
+              const float tv = lv[i][s]; lv[i][s] = lv[i][s - 1]; lv[i][s - 1] = tv;
+              const int ti = li[i][s]; li[i][s] = li[i][s - 1]; li[i][s - 1] = ti;
+            }
           }
         }
       }
     }
   }
 
-  int hits = 0;
-  const int64_t ql = active ? qlab[row] : 0;
-  for (int r = 0; r < k; ++r) {
-    float bv = lv[0];
-    int bi = li[0];
+  // ---- this CTA's top-k of each query (k rounds of a warp arg-max over the lane lists)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
-    }
-    if (li[0] == bi) {  // the winner pops its head
+  for (int i = 0; i < QW; ++i) {
+    for (int r = 0; r < k; ++r) {
+      float bv = lv[i][0];
+      int bi = li[i][0];
 #pragma unroll
-      for (int s = 0; s + 1 < KMAX; ++s) lv[s] = lv[s + 1], li[s] = li[s + 1];
-      lv[KMAX - 1] = -INFINITY;
-      li[KMAX - 1] = 0x7fffffff;
-    }
-    if (active && lane == 0) {
-      const bool found = bi != 0x7fffffff;
-      const int64_t lab = found ? plab[bi] : -1;
-      topk_labels[row * k + r] = lab;
-      if (topk_index) topk_index[row * k + r] = found ? bi : -1;
-      hits += found && lab == ql;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+      }
+      if (li[i][0] == bi) {  // the winner pops its head
+#pragma unroll
+        for (int s = 0; s + 1 < KMAX; ++s) lv[i][s] = lv[i][s + 1], li[i][s] = li[i][s + 1];
+        lv[i][KMAX - 1] = -INFINITY;
+        li[i][KMAX - 1] = 0x7fffffff;
+      }
+      if (lane == 0) s_val[warp * QW + i][r] = bv, s_idx[warp * QW + i][r] = bi;
     }
   }
-  if (lane == 0 && hits) atomicAdd(hit_count, hits);
-  if (lane == 0 && active) atomicAdd(hit_count + 1, 1);   // queries that took part
+  cluster.sync();
+
+  // ---- cluster rank 0 merges the 8 sorted lists of each query: lane l holds the list of CTA l
+  if (rank == 0) {
+    int hits = 0, took_part = 0;
+#pragma unroll
+    for (int i = 0; i < QW; ++i) {
+      float mv[KMAX];
+      int mi[KMAX];
+#pragma unroll
+      for (int s = 0; s < KMAX; ++s) mv[s] = -INFINITY, mi[s] = 0x7fffffff;
+      if (lane < kTopkCluster) {
+        const float* rv = cluster.map_shared_rank(&s_val[warp * QW + i][0], lane);
+        const int* ri = cluster.map_shared_rank(&s_idx[warp * QW + i][0], lane);
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s)
+          if (s < k) mv[s] = rv[s], mi[s] = ri[s];
+      }
+      const int64_t row = row0 + i;
+      const int64_t ql = active[i] ? qlab[row] : 0;
+      for (int r = 0; r < k; ++r) {
+        float bv = mv[0];
+        int bi = mi[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+        }
+        if (mi[0] == bi) {
+#pragma unroll
+          for (int s = 0; s + 1 < KMAX; ++s) mv[s] = mv[s + 1], mi[s] = mi[s + 1];
+          mv[KMAX - 1] = -INFINITY;
+          mi[KMAX - 1] = 0x7fffffff;
+        }
+        if (active[i] && lane == 0) {
+          const bool found = bi != 0x7fffffff;
+          const int64_t lab = found ? plab[bi] : -1;
+          topk_labels[row * k + r] = lab;
+          if (topk_index) topk_index[row * k + r] = found ? bi : -1;
+          hits += found && lab == ql;
+        }
+      }
+      took_part += active[i] ? 1 : 0;
+    }
+    if (lane == 0 && hits) atomicAdd(hit_count, hits);
+    if (lane == 0 && took_part) atomicAdd(hit_count + 1, took_part);   // queries that took part
+  }
+  cluster.sync();   // the other CTAs' shared memory stays alive until rank 0 has read it
 }
 
 }  // namespace spml
@@ -117,20 +216,31 @@ int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int
   SPML_CUDA(cudaMemsetAsync(hit_count, 0, 2 * sizeof(int32_t), st));
   if (nq == 0) return SPML_OK;
   SPML_CHECK_ARG(q && p && qlab && plab && topk_labels, "topk_ranking: null pointer");
-  const size_t smem = ((size_t)kTopkWarps * dim + (size_t)kTopkCols * (dim + 1)) * sizeof(float);
-  const unsigned blocks = (unsigned)ceil_div(nq, kTopkWarps);
+  const int qw = k <= 8 ? 4 : 1;   // query rows per warp (the long lists of k > 8 leave no registers)
+  const size_t smem = ((size_t)kTopkWarps * qw * ((dim + 3) & ~3) + (size_t)kTopkCols * (dim + 1)) *
+                      sizeof(float);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ceil_div(nq, kTopkWarps * qw) * kTopkCluster));
+  cfg.blockDim = dim3(kTopkWarps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kTopkCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (k <= 8) {
-    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    topk_kernel<8><<<blocks, kTopkWarps * 32, smem, st>>>(q, nq, p, m, dim, qlab, plab, qvalid,
-                                                          pvalid, k, topk_labels, topk_index,
-                                                          hit_count);
+    SPML_CUDA(cudaLaunchKernelEx(&cfg, topk_kernel<8, 4>, q, nq, p, m, dim, qlab, plab, qvalid,
+                                 pvalid, k, topk_labels, topk_index, hit_count));
   } else {
-    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    topk_kernel<32><<<blocks, kTopkWarps * 32, smem, st>>>(q, nq, p, m, dim, qlab, plab, qvalid,
-                                                           pvalid, k, topk_labels, topk_index,
-                                                           hit_count);
+    SPML_CUDA(cudaLaunchKernelEx(&cfg, topk_kernel<32, 1>, q, nq, p, m, dim, qlab, plab, qvalid,
+                                 pvalid, k, topk_labels, topk_index, hit_count));
   }
   SPML_LAUNCH_CHECK("topk_kernel");
   return SPML_OK;

@@ -81,6 +81,28 @@ def test_kmeans_matches_oracle(n, dim, k):
   assert int((got != want).sum()) == 0
 
 
+@pytest.mark.parametrize('n,dim,k,batch', [(5000, 66, 36, 1), (20000, 66, 36, 3), (3000, 37, 300, 1),
+                                           (9000, 128, 1000, 1), (4097, 64, 129, 2),
+                                           (130, 16, 7, 1)])
+def test_kmeans_tensor_core_equals_fp32(n, dim, k, batch, monkeypatch):
+  """The tcgen05 E-step (with its exact re-check of near-ties) and the fp32 CUDA-core
+  E-step return identical labels, also on data with no cluster structure (many near-ties)."""
+  g = torch.Generator().manual_seed(7 * n + dim)
+  for noise in (0.7, 30.0):
+    centres = torch.randn(k, dim, generator=g)
+    cell = torch.arange(n) * k // n
+    e = O.l2_normalize(centres[cell] + noise * torch.randn(n, dim, generator=g)).cuda()
+    lab0 = cell[torch.randperm(n, generator=g)].to(torch.int32).cuda()
+    per = (n + batch - 1) // batch
+    img_off = torch.tensor([min(i * per, n) for i in range(batch + 1)], dtype=torch.int32).cuda()
+    got = {}
+    for path in ('fp32', 'tc'):
+      monkeypatch.setenv('SPML_B200_KMEANS', path)
+      got[path], _ = ops.kmeans(e, img_off, batch, per, k, 10, lab0, want_i64=False)
+      torch.cuda.synchronize()
+    assert torch.equal(got['fp32'], got['tc']), int((got['fp32'] != got['tc']).sum())
+
+
 def test_prepare_prototype_labels(units):
   u = units['prototype_labels']
   plab, inv = segsort_common.prepare_prototype_labels(cu(u['sem']), cu(u['inst']), 256)
