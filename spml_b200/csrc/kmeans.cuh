@@ -63,7 +63,7 @@ __device__ __forceinline__ void split_fixed(float v, int& hi, int& lo) {
 }
 
 constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
-constexpr int kKmReplicas = 4;   // copies of the segment sums in the tensor-core path
+constexpr int kKmReplicas = 2;   // copies of the segment sums in the tensor-core path
 
 // kmeans_tc.cu
 bool kmeans_tc_supported(int dim);

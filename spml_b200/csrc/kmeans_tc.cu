@@ -71,6 +71,15 @@ struct KmeansTcArgs {
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
+// __threadfence() compiles to MEMBAR.SC.GPU + CCTL.IVALL here; acquire / release is enough
+__device__ __forceinline__ void fence_acq_rel_gpu() {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------- M-step pieces
 
@@ -99,6 +108,7 @@ __device__ __forceinline__ void rank_rows_by_label(const int* s_lab, int rows, i
 // adds a run to the image's sums whenever the label changes: about (labels in the tile + 8)
 // flushes per tile.  A value is round(x * 2^32) kept as hi * 2^16 + lo in two exact 32-bit
 // integers (at most 16 rows per run: neither half can overflow).
+template <int kSlots>
 __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows, const float* xs,
                                                   const int* s_lab, const unsigned char* s_order,
                                                   long long* __restrict__ sums_b) {
@@ -106,15 +116,15 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
   const int dim = p.dim;
   constexpr int kPer = BM / kKmWarps;   // 16
   const int e0 = warp * kPer;
-  int run_hi[kAccSlots], run_lo[kAccSlots];
+  int run_hi[kSlots], run_lo[kSlots];
 #pragma unroll
-  for (int s = 0; s < kAccSlots; ++s) run_hi[s] = run_lo[s] = 0;
+  for (int s = 0; s < kSlots; ++s) run_hi[s] = run_lo[s] = 0;
   int run_lab = -1;
   bool bad = false;
   auto flush = [&]() {
     if (run_lab < 0) return;
 #pragma unroll
-    for (int s = 0; s < kAccSlots; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       const int d = lane + 32 * s;
       if (d < dim && (run_hi[s] | run_lo[s]) != 0)
         atomic_add_i64(&sums_b[(int64_t)run_lab * dim + d],
@@ -125,7 +135,7 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
 #pragma unroll
   for (int g = 0; g < kPer / 4; ++g) {
     // four rows in flight: all their shared-memory loads are issued before the first add
-    float v[4][kAccSlots];
+    float v[4][kSlots];
     int lab4[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -134,7 +144,7 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
       const int row = ok ? s_order[e] : 0;
       lab4[u] = ok ? s_lab[row] : -1;
 #pragma unroll
-      for (int s = 0; s < kAccSlots; ++s) {
+      for (int s = 0; s < kSlots; ++s) {
         const int d = lane + 32 * s;
         v[u][s] = (ok && d < dim) ? xs[row * dim + d] : 0.f;
       }
@@ -147,7 +157,7 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
         run_lab = lab4[u];
       }
 #pragma unroll
-      for (int s = 0; s < kAccSlots; ++s) {
+      for (int s = 0; s < kSlots; ++s) {
         bad |= !(fabsf(v[u][s]) <= 8.f);
         int hi, lo;
         split_fixed(v[u][s], hi, lo);
@@ -160,21 +170,23 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
   if (bad) *p.poison = 1;
 }
 
-// sums of the R replicas -> `stage` (shared memory), four elements per thread in flight
+// sums of the R replicas -> `stage` (shared memory); kE elements per thread in flight, so the
+// K x dim words of the shipped configurations take ONE round trip to L2
 template <int R>
 __device__ __forceinline__ void stage_sums(const long long* __restrict__ sums_it, size_t per_iter,
                                            int n, long long* stage) {
+  constexpr int kE = 10;
   const int tid = threadIdx.x;
-  for (int base = 0; base < n; base += 4 * kGemmThreads) {
-    long long v[4][R];
+  for (int base = 0; base < n; base += kE * kGemmThreads) {
+    long long v[kE][R];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kE; ++j) {
       const int i = base + j * kGemmThreads + tid;
 #pragma unroll
       for (int r = 0; r < R; ++r) v[j][r] = i < n ? __ldcg(sums_it + (size_t)r * per_iter + i) : 0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kE; ++j) {
       const int i = base + j * kGemmThreads + tid;
       long long t = v[j][0];
 #pragma unroll
@@ -185,10 +197,10 @@ __device__ __forceinline__ void stage_sums(const long long* __restrict__ sums_it
 }
 
 // unit prototypes from the (folded) sums: fp32 rows for the exact re-check and bf16 hi / lo
-// rows of dp columns (zero beyond dim) for the TMA-fed operand.  common.py:39:
+// rows of dp columns for the TMA-fed operand.  common.py:39:
 // sum / max(||sum||, eps); an empty cluster is the zero vector.  Four prototypes per warp
 // and round, their loads and shuffles interleaved.
-template <bool kGlobal>
+template <bool kGlobal, int kSlots>
 __device__ __forceinline__ void normalise_write(const KmeansArgs& p, const long long* sums, int kb,
                                                 float* __restrict__ out,
                                                 __nv_bfloat16* __restrict__ out_hi,
@@ -196,13 +208,13 @@ __device__ __forceinline__ void normalise_write(const KmeansArgs& p, const long 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dim = p.dim;
   for (int kbase = 0; kbase < kb; kbase += 4 * kKmWarps) {
-    float v[4][kMaxSlots], ss[4];
+    float v[4][kSlots], ss[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = kbase + warp + i * kKmWarps;
       ss[i] = 0.f;
 #pragma unroll
-      for (int s = 0; s < kMaxSlots; ++s) {
+      for (int s = 0; s < kSlots; ++s) {
         const int d = lane + 32 * s;
         long long raw = 0;
         if (k < kb && d < dim)
@@ -222,21 +234,30 @@ __device__ __forceinline__ void normalise_write(const KmeansArgs& p, const long 
       const float div = nrm >= p.eps ? nrm : p.eps;
       if (k < kb) {
 #pragma unroll
-        for (int s = 0; s < kMaxSlots; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
           const int d = lane + 32 * s;
-          const float u = v[i][s] / div;
-          if (d < dim) out[(int64_t)k * dim + d] = u;
-          if (d < dp) {
-            const float z = d < dim ? u : 0.f;
-            const __nv_bfloat16 h = __float2bfloat16_rn(z);
+          if (d < dim) {   // the columns [dim, dp) of the bf16 rows were zeroed by the host
+            const float u = v[i][s] / div;
+            out[(int64_t)k * dim + d] = u;
+            const __nv_bfloat16 h = __float2bfloat16_rn(u);
             out_hi[(int64_t)k * dp + d] = h;
-            out_lo[(int64_t)k * dp + d] = __float2bfloat16_rn(z - __bfloat162float(h));
+            out_lo[(int64_t)k * dp + d] = __float2bfloat16_rn(u - __bfloat162float(h));
           }
         }
       }
     }
   }
 }
+
+// the channel loops are unrolled over ceil(dim / 32) slots per lane
+#define KM_SLOT_SWITCH(dim, CALL)            \
+  switch (((dim) + 31) >> 5) {               \
+    case 1: { constexpr int kS = 1; CALL; } break; \
+    case 2: { constexpr int kS = 2; CALL; } break; \
+    case 3: { constexpr int kS = 3; CALL; } break; \
+    case 4: { constexpr int kS = 4; CALL; } break; \
+    default: { constexpr int kS = 5; CALL; } break; \
+  }
 
 // ------------------------------------------------------------------------- the kernel
 
@@ -370,10 +391,9 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
       } else {
         // ================================================================== E-step
         if (tid == 0) {
-          volatile unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
-          while (*flag == 0) {
+          const unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
+          while (ld_acquire_gpu(flag) == 0) {
           }
-          __threadfence();
           s_namb = 0;
         }
         __syncthreads();
@@ -543,15 +563,16 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         long long* sums_b = sums_it + (size_t)(blockIdx.x % p.replicas) * per_iter;
         rank_rows_by_label(s_lab, tile.rows, s_rank, s_order);
         KMT(11);
-        accumulate_ranked(p, tile.rows, xs, s_lab, s_order, sums_b);
+        KM_SLOT_SWITCH(dim, (accumulate_ranked<kS>(p, tile.rows, xs, s_lab, s_order, sums_b)));
         __syncthreads();
         KMT(8);
         if (tid == 0) {
           const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
                                                      : p.rows_total);
           const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
-          __threadfence();
+          fence_acq_rel_gpu();   // cumulative: the CTA's reductions (ordered by the barrier) first
           s_last = atomicAdd(p.done + (size_t)it * p.batch + b, 1u) + 1 == tiles_b;
+          fence_acq_rel_gpu();
         }
         __syncthreads();
         KMT(9);
@@ -559,7 +580,6 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         if (s_last) {
           // ---- the image's last tile is in: fold the replicas, normalise, publish
           KMT_FIN(10);
-          __threadfence();
           KMT_FIN(11);
           const size_t slab = ((size_t)it * p.batch + b) * p.num_clusters * dp;
           float* out = p.protos + (size_t)it * per_iter + b * per_img;
@@ -570,7 +590,8 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
             stage_sums<kKmReplicas>(sums_it, per_iter, n, stage);
             __syncthreads();
             KMT_FIN(12);
-            normalise_write<false>(p, stage, kb, out, a.ph + slab, a.pl + slab, dp);
+            KM_SLOT_SWITCH(dim, (normalise_write<false, kS>(p, stage, kb, out, a.ph + slab,
+                                                            a.pl + slab, dp)));
           } else {
             for (int i = tid; i < n; i += kGemmThreads) {   // fold into copy 0 in place
               long long v = 0;
@@ -580,14 +601,17 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
             __threadfence_block();
             __syncthreads();
             KMT_FIN(12);
-            normalise_write<true>(p, sums_it, kb, out, a.ph + slab, a.pl + slab, dp);
+            KM_SLOT_SWITCH(dim, (normalise_write<true, kS>(p, sums_it, kb, out, a.ph + slab,
+                                                           a.pl + slab, dp)));
           }
           KMT_FIN(13);
-          __threadfence();
-          KMT_FIN(14);
           fence_proxy_async_all();   // the consumers read the bf16 rows through TMA
           __syncthreads();
-          if (tid == 0) atomicExch(p.ready + (size_t)it * p.batch + b, 1u);
+          KMT_FIN(14);
+          if (tid == 0) {
+            fence_acq_rel_gpu();     // cumulative over the CTA's stores (ordered by the barrier)
+            atomicExch(p.ready + (size_t)it * p.batch + b, 1u);
+          }
           KMT_CTA(3);
           KMT_FIN(15);
         }
@@ -652,6 +676,8 @@ int kmeans_tc_launch(const KmeansArgs& p, void* split_protos, int sms, cudaStrea
   SPML_CHECK_SUPPORTED(split_rows < (1ull << 31), "kmeans: too many prototype rows");
   a.ph = reinterpret_cast<__nv_bfloat16*>(split);
   a.pl = reinterpret_cast<__nv_bfloat16*>(split + split_bytes);
+  // K padding of the bf16 rows (columns [dim, 64 nkb)): zero x garbage could be NaN
+  if (p.dim < a.nkb * 64) SPML_CUDA(cudaMemsetAsync(split, 0, 2 * split_bytes, st));
   CUtensorMap map_ph, map_pl;
   const uint64_t pitch = (uint64_t)a.nkb * 64 * 2;
   int rc;
