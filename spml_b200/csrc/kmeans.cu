@@ -315,12 +315,18 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
       256);
 }
 
-// The E-step runs on the tensor cores whenever the shape is supported;
+// Which E-step runs (both return the same labels, bit for bit).  Measured on B200
+// (profiles/r1c_*): the tcgen05 kernel (one CTA per SM, every phase of a tile in sequence) wins
+// when each CTA keeps its one tile resident, and when the assignment GEMM is big (K >= 512, or
+// K >= 256 with many tiles per SM); with a few tiles per SM and K < 256 the fp32 kernel's
+// 2-4 co-resident CTAs per SM hide the per-tile latencies better.
 // SPML_B200_KMEANS=fp32|tc overrides (read per call so that tests can compare the two).
-static bool kmeans_use_tc(int dim) {
+static bool kmeans_use_tc(int dim, int num_clusters, int64_t tiles, int sms) {
   if (!spml::kmeans_tc_supported(dim)) return false;
   const char* e = getenv("SPML_B200_KMEANS");
-  return !(e && !strcmp(e, "fp32"));
+  if (e && !strcmp(e, "fp32")) return false;
+  if (e && !strcmp(e, "tc")) return true;
+  return tiles <= sms || num_clusters >= 512 || (num_clusters >= 256 && tiles >= 8ll * sms);
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {
@@ -354,7 +360,11 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
     set_error("kmeans: workspace %zu < %zu bytes", workspace_bytes, need);
     return SPML_E_WORKSPACE;
   }
-  const bool use_tc = kmeans_use_tc(dim);
+  int device = 0, sms = 0, per_sm = 0;
+  SPML_CUDA(cudaGetDevice(&device));
+  SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const bool use_tc =
+      kmeans_use_tc(dim, num_clusters, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
   const int replicas = use_tc ? kKmReplicas : 1;
   const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, replicas);
   SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
@@ -382,9 +392,6 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.labels_out64 = labels_out_i64;
   p.eps = 1e-12f;
 
-  int device = 0, sms = 0, per_sm = 0;
-  SPML_CUDA(cudaGetDevice(&device));
-  SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if (use_tc)
     return kmeans_tc_launch(p, base + kmeans_split_offset(batch, num_clusters, dim, iterations),
                             sms, st);

@@ -170,73 +170,62 @@ __device__ __forceinline__ void accumulate_ranked(const KmeansArgs& p, int rows,
   if (bad) *p.poison = 1;
 }
 
-// sums of the R replicas -> `stage` (shared memory); kE elements per thread in flight, so the
-// K x dim words of the shipped configurations take ONE round trip to L2
-template <int R>
-__device__ __forceinline__ void stage_sums(const long long* __restrict__ sums_it, size_t per_iter,
-                                           int n, long long* stage) {
-  constexpr int kE = 10;
-  const int tid = threadIdx.x;
-  for (int base = 0; base < n; base += kE * kGemmThreads) {
-    long long v[kE][R];
-#pragma unroll
-    for (int j = 0; j < kE; ++j) {
-      const int i = base + j * kGemmThreads + tid;
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[j][r] = i < n ? __ldcg(sums_it + (size_t)r * per_iter + i) : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < kE; ++j) {
-      const int i = base + j * kGemmThreads + tid;
-      long long t = v[j][0];
-#pragma unroll
-      for (int r = 1; r < R; ++r) t += v[j][r];
-      if (i < n) stage[i] = t;
-    }
-  }
-}
-
-// unit prototypes from the (folded) sums: fp32 rows for the exact re-check and bf16 hi / lo
-// rows of dp columns for the TMA-fed operand.  common.py:39:
-// sum / max(||sum||, eps); an empty cluster is the zero vector.  Four prototypes per warp
-// and round, their loads and shuffles interleaved.
-template <bool kGlobal, int kSlots>
-__device__ __forceinline__ void normalise_write(const KmeansArgs& p, const long long* sums, int kb,
-                                                float* __restrict__ out,
-                                                __nv_bfloat16* __restrict__ out_hi,
-                                                __nv_bfloat16* __restrict__ out_lo, int dp) {
+// The image's last tile is in: unit prototypes from the sums (common.py:39:
+// sum / max(||sum||, eps); an empty cluster is the zero vector).  One warp per prototype,
+// lanes across the channels; the loads of five prototypes x R replicas are all in flight
+// together, so the K x dim words of the shipped configurations cost ONE round trip to L2.
+// Writes the fp32 rows (exact re-check) and the bf16 hi / lo rows (TMA-fed operand; their
+// padding columns [dim, dp) were zeroed by the host).
+template <int kSlots, int R>
+__device__ __forceinline__ void finalize_image(const KmeansArgs& p,
+                                               const long long* __restrict__ sums_it,
+                                               size_t per_iter, int kb, float* __restrict__ out,
+                                               __nv_bfloat16* __restrict__ out_hi,
+                                               __nv_bfloat16* __restrict__ out_lo, int dp) {
+  constexpr int kC = 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dim = p.dim;
-  for (int kbase = 0; kbase < kb; kbase += 4 * kKmWarps) {
-    float v[4][kSlots], ss[4];
+  for (int kbase = warp; kbase < kb; kbase += kC * kKmWarps) {
+    long long raw[kC][kSlots][R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = kbase + warp + i * kKmWarps;
-      ss[i] = 0.f;
+    for (int i = 0; i < kC; ++i) {
+      const int k = kbase + i * kKmWarps;
 #pragma unroll
       for (int s = 0; s < kSlots; ++s) {
         const int d = lane + 32 * s;
-        long long raw = 0;
-        if (k < kb && d < dim)
-          raw = kGlobal ? __ldcg(sums + (int64_t)k * dim + d) : sums[(int64_t)k * dim + d];
-        v[i][s] = fixed_to_float(raw);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          raw[i][s][r] = (k < kb && d < dim)
+                             ? __ldcg(sums_it + (size_t)r * per_iter + (size_t)k * dim + d) : 0;
+      }
+    }
+    float v[kC][kSlots], ss[kC];
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      ss[i] = 0.f;
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s) {
+        long long t = raw[i][s][0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) t += raw[i][s][r];
+        v[i][s] = fixed_to_float(t);
         ss[i] += v[i][s] * v[i][s];
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+      for (int i = 0; i < kC; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = kbase + warp + i * kKmWarps;
+    for (int i = 0; i < kC; ++i) {
+      const int k = kbase + i * kKmWarps;
       const float nrm = sqrtf(ss[i]);
       const float div = nrm >= p.eps ? nrm : p.eps;
       if (k < kb) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const int d = lane + 32 * s;
-          if (d < dim) {   // the columns [dim, dp) of the bf16 rows were zeroed by the host
+          if (d < dim) {
             const float u = v[i][s] / div;
             out[(int64_t)k * dim + d] = u;
             const __nv_bfloat16 h = __float2bfloat16_rn(u);
@@ -519,32 +508,62 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         const int namb = s_namb;
         KMT(6);
         const float* __restrict__ protos_b = p.protos + (size_t)(it - 1) * per_iter + b * per_img;
-        for (int i = warp; i < namb; i += kKmWarps) {
-          const int r = s_amb[i];
-          const float* xr = xs + r * dim;
-          float bv = -INFINITY;
-          int bk = 0;
-          for (int k = lane; k < kb; k += 32) {
-            const float* pk = protos_b + (size_t)k * dim;
-            float accv = 0.f;
-            int d = 0;
-            for (; d + 8 <= dim; d += 8) {   // eight loads in flight, the fmaf chain in order
-              float pv[8];
+        if (namb > 0) {   // block-uniform
+          // The MMAs of this tile are complete, so the prototype ring is idle: stage the
+          // image's fp32 prototypes in it (one coalesced pass) instead of chasing them through
+          // L2 element by element (measured: tiles with near-ties took 2x as long).
+          const bool in_smem = (size_t)kb * dim * sizeof(float) <= (size_t)a.stages * stage_bytes;
+          float* pf = reinterpret_cast<float*>(b_ring);
+          if (in_smem) {
+            const int n = kb * dim;
+            for (int i0 = 0; i0 < n; i0 += 8 * kGemmThreads) {
+              float r8[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) pv[u] = __ldcg(pk + d + u);
+              for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * kGemmThreads + tid;
+                r8[j] = i < n ? __ldcg(protos_b + i) : 0.f;
+              }
 #pragma unroll
-              for (int u = 0; u < 8; ++u) accv = fmaf(xr[d + u], pv[u], accv);
+              for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * kGemmThreads + tid;
+                if (i < n) pf[i] = r8[j];
+              }
             }
-            for (; d < dim; ++d) accv = fmaf(xr[d], __ldcg(pk + d), accv);
-            if (accv > bv) bv = accv, bk = k;
+            __syncthreads();
           }
+          for (int i = warp; i < namb; i += kKmWarps) {
+            const int r = s_amb[i];
+            const float* xr = xs + r * dim;
+            float bv = -INFINITY;
+            int bk = 0;
+            for (int k = lane; k < kb; k += 32) {
+              float accv = 0.f;
+              if (in_smem) {
+                const float* pk = pf + k * dim;
+#pragma unroll 4
+                for (int d = 0; d < dim; ++d) accv = fmaf(xr[d], pk[d], accv);
+              } else {
+                const float* pk = protos_b + (size_t)k * dim;
+                int d = 0;
+                for (; d + 8 <= dim; d += 8) {   // eight loads in flight, the fmaf chain in order
+                  float pv[8];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (ov > bv || (ov == bv && ok < bk)) bv = ov, bk = ok;
+                  for (int u = 0; u < 8; ++u) pv[u] = __ldcg(pk + d + u);
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) accv = fmaf(xr[d + u], pv[u], accv);
+                }
+                for (; d < dim; ++d) accv = fmaf(xr[d], __ldcg(pk + d), accv);
+              }
+              if (accv > bv) bv = accv, bk = k;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+              if (ov > bv || (ov == bv && ok < bk)) bv = ov, bk = ok;
+            }
+            if (lane == 0) s_lab[r] = bk;
           }
-          if (lane == 0) s_lab[r] = bk;
         }
         __syncthreads();
         KMT(7);
@@ -583,27 +602,8 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
           KMT_FIN(11);
           const size_t slab = ((size_t)it * p.batch + b) * p.num_clusters * dp;
           float* out = p.protos + (size_t)it * per_iter + b * per_img;
-          const int n = kb * dim;
-          if ((size_t)n * sizeof(long long) <= stage_bytes) {
-            // the prototype ring is idle here: stage the folded sums in it
-            long long* stage = reinterpret_cast<long long*>(b_ring);
-            stage_sums<kKmReplicas>(sums_it, per_iter, n, stage);
-            __syncthreads();
-            KMT_FIN(12);
-            KM_SLOT_SWITCH(dim, (normalise_write<false, kS>(p, stage, kb, out, a.ph + slab,
-                                                            a.pl + slab, dp)));
-          } else {
-            for (int i = tid; i < n; i += kGemmThreads) {   // fold into copy 0 in place
-              long long v = 0;
-              for (int r = 0; r < p.replicas; ++r) v += __ldcg(sums_it + (size_t)r * per_iter + i);
-              sums_it[i] = v;
-            }
-            __threadfence_block();
-            __syncthreads();
-            KMT_FIN(12);
-            KM_SLOT_SWITCH(dim, (normalise_write<true, kS>(p, sums_it, kb, out, a.ph + slab,
-                                                           a.pl + slab, dp)));
-          }
+          KM_SLOT_SWITCH(dim, (finalize_image<kS, kKmReplicas>(p, sums_it, per_iter, kb, out,
+                                                               a.ph + slab, a.pl + slab, dp)));
           KMT_FIN(13);
           fence_proxy_async_all();   // the consumers read the bf16 rows through TMA
           __syncthreads();

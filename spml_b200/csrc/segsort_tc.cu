@@ -473,6 +473,8 @@ struct TcBwdArgs {
   const int32_t* ccode;
   const float* stats;
   const float* grad_loss;
+  float4* pm;                 // [n_rows] per-pixel gradient weights: written by the pixel-owner
+                              // kernel (or pix_meta_kernel), read by the prototype-owner kernel
   float* out;                 // demb, or the [chunks][m][dim] prototype partials
   int64_t ld_out;
   float beta;
@@ -503,6 +505,18 @@ __device__ __forceinline__ PixMeta load_pix_meta(const TcBwdArgs& a, int64_t r, 
   pm.w01 = pos ? coef * inv_num : coef * (2.f * inv_den - inv_num);
   pm.w11 = pos ? 0.f : coef * (inv_den - inv_num);
   return pm;
+}
+
+// the weights of every live row, for a backward call that asks for d(prototypes) only
+__global__ void pix_meta_kernel(const TcBwdArgs a) {
+  const int g = blockIdx.y;
+  const spml_segsort_desc& d = a.d;
+  const int64_t r_begin = d.group_off ? d.group_off[g] : 0;
+  const int64_t r_end = d.group_off ? d.group_off[g + 1] : d.n_rows;
+  const int64_t r = r_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= r_end) return;
+  const PixMeta pm = load_pix_meta(a, r, reduction_weight(d, g));
+  a.pm[r] = make_float4(pm.w00, pm.w10, pm.w01, pm.w11);
 }
 
 template <int kMode>
@@ -630,21 +644,33 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     }
     for (int j = 0; j < ntiles; ++j) {
       const int s = j % a.stages, use = j / a.stages;
-      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
       const int64_t s0 = s_lo + (int64_t)j * kBwdBN;
       int seg_min = 0x7fffffff, seg_max = -1;
-      for (int k = lane; k < kBwdBN; k += 32) {
-        const int64_t e = s0 + k;
+      // the tile's metadata does not depend on the ring slot: fetch it (both halves of the 64
+      // entries at once) while the slot is still busy
+      int code2[2], seg2[2];
+      float4 pm2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t e = s0 + lane + 32 * h;
         const bool in = e < s_hi;
         if (!kProtoOwner) {
-          s_code[s][k] = in ? a.ccode[e] : 0;
+          code2[h] = in ? a.ccode[e] : 0;
         } else {
-          const int sg = in ? a.rseg[e] : -1;
-          s_code[s][k] = in ? a.rcode[e] : 0;
-          s_seg[s][k] = sg;
-          PixMeta z = {0.f, 0.f, 0.f, 0.f};
-          s_pm[s][k] = in ? load_pix_meta(a, e, weight) : z;
-          if (in) seg_min = min(seg_min, sg), seg_max = max(seg_max, sg);
+          code2[h] = in ? a.rcode[e] : 0;
+          seg2[h] = in ? a.rseg[e] : -1;
+          pm2[h] = in ? a.pm[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        s_code[s][k] = code2[h];
+        if (kProtoOwner) {
+          s_seg[s][k] = seg2[h];
+          *reinterpret_cast<float4*>(&s_pm[s][k]) = pm2[h];
+          if (seg2[h] >= 0) seg_min = min(seg_min, seg2[h]), seg_max = max(seg_max, seg2[h]);
         }
       }
       if (kProtoOwner) {
@@ -802,6 +828,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         code_o = a.rcode[orow];
         seg_o = a.rseg[orow];
         pm_o = load_pix_meta(a, orow, weight);
+        if (half == 0 && a.pm) a.pm[orow] = make_float4(pm_o.w00, pm_o.w10, pm_o.w01, pm_o.w11);
       } else {
         code_o = a.ccode[orow];
       }
@@ -1021,6 +1048,7 @@ TcPlan segsort_tc_plan(const spml_segsort_desc& d, void* base) {
   p.col_dst = reinterpret_cast<int32_t*>(take((size_t)d.m * 4));
   p.col_src = reinterpret_cast<int32_t*>(take((size_t)d.m * 4));
   p.col_count = reinterpret_cast<int32_t*>(take(16));
+  p.pm = reinterpret_cast<float4*>(take((size_t)d.n_rows * sizeof(float4)));
   p.bytes = off;
   return p;
 }
@@ -1124,6 +1152,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.ccode = p.ccode;
   a.stats = stats;
   a.grad_loss = grad_loss;
+  a.pm = p.pm;
   a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
   a.nkb = p.nkb;
   a.ksteps = p.ksteps;
@@ -1179,6 +1208,12 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<emb>");
   }
   if (proto_partial) {
+    if (!demb) {   // nobody has written the per-pixel weights yet
+      dim3 pgrid((unsigned)std::max<int64_t>(1, ceil_div(d.max_rows_per_group, 256)),
+                 (unsigned)d.num_groups);
+      pix_meta_kernel<<<pgrid, 256, 0, st>>>(a);
+      SPML_LAUNCH_CHECK("pix_meta_kernel");
+    }
     if ((rc = make_tensor_map_bf16_2d(&p128h, p.ph, p.dp, d.m, pitch, 64, kBwdBM))) return rc;
     if ((rc = make_tensor_map_bf16_2d(&p128l, p.pl, p.dp, d.m, pitch, 64, kBwdBM))) return rc;
     if ((rc = make_tensor_map_bf16_2d(&e64h, p.eh, p.dp, d.n_rows, pitch, 64, kBwdBN))) return rc;

@@ -17,6 +17,7 @@ struct TcPlan {
   __nv_bfloat16 *eh, *el, *ph, *pl;
   int32_t *rcode, *rseg, *ccode;
   int32_t *col_dst, *col_src, *col_count;
+  float4* pm;   // [n_rows] per-pixel gradient weights of the backward pass
   size_t bytes;
 };
 
