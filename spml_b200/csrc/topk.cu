@@ -64,16 +64,70 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
 #pragma unroll
     for (int s = 0; s < KMAX; ++s) lv[i][s] = -INFINITY, li[i][s] = 0x7fffffff;
 
-  for (int64_t c0 = (int64_t)rank * kTopkCols; c0 < m; c0 += kTopkCluster * kTopkCols) {
+  // Which of this CTA's column tiles hold a live prototype (fixed-capacity banks are mostly
+  // padding): one batch of loads up front instead of a dependent L2 round trip per tile.
+  constexpr int kMaxTiles = 64;
+  __shared__ int s_live[kMaxTiles];
+  const int64_t stride = (int64_t)kTopkCluster * kTopkCols;
+  const int64_t first = (int64_t)rank * kTopkCols;
+  const int my_tiles = first < m ? (int)((m - first + stride - 1) / stride) : 0;
+  const bool mask_known = pvalid && my_tiles <= kMaxTiles;
+  if (mask_known) {
+    if (threadIdx.x < kMaxTiles) s_live[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < my_tiles * kTopkCols; i0 += 4 * kTopkWarps * 32) {
+      uint8_t f[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i0 + u * kTopkWarps * 32 + threadIdx.x;
+        const int64_t c = first + (int64_t)(idx >> 6) * stride + (idx & 63);
+        f[u] = (idx < my_tiles * kTopkCols && c < m) ? pvalid[c] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i0 + u * kTopkWarps * 32 + threadIdx.x;
+        if (f[u]) s_live[idx >> 6] = 1;
+      }
+    }
+    __syncthreads();
+  }
+
+  int tile = 0;
+  for (int64_t c0 = first; c0 < m; c0 += stride, ++tile) {
     const int cc = (int)min((int64_t)kTopkCols, m - c0);
-    if (pvalid) {   // skip tiles made of dead columns only (block-uniform)
+    if (mask_known) {
+      if (!s_live[tile]) continue;   // block-uniform
+    } else if (pvalid) {
       const bool live = threadIdx.x < cc && pvalid[c0 + threadIdx.x];
       if (!__syncthreads_or(live)) continue;
     }
     __syncthreads();
-    for (int j = warp; j < kTopkCols; j += kTopkWarps)
-      for (int d = lane; d < dim; d += 32)
-        Ps[j * ldp + d] = j < cc ? p[(c0 + j) * dim + d] : 0.f;
+    if (dim <= 128) {
+      // eight prototype rows per warp, all their loads in flight before the first store
+      float v[kTopkCols / kTopkWarps][4];
+#pragma unroll
+      for (int i = 0; i < kTopkCols / kTopkWarps; ++i) {
+        const int j = warp + i * kTopkWarps;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int d = lane + 32 * u;
+          v[i][u] = (j < cc && d < dim) ? p[(c0 + j) * dim + d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kTopkCols / kTopkWarps; ++i) {
+        const int j = warp + i * kTopkWarps;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int d = lane + 32 * u;
+          if (d < dim) Ps[j * ldp + d] = v[i][u];
+        }
+      }
+    } else {
+      for (int j = warp; j < kTopkCols; j += kTopkWarps)
+        for (int d = lane; d < dim; d += 32)
+          Ps[j * ldp + d] = j < cc ? p[(c0 + j) * dim + d] : 0.f;
+    }
     __syncthreads();
     float acc[QW][2];
 #pragma unroll

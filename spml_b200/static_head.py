@@ -87,9 +87,11 @@ class StaticContrastiveHead(nn.Module):
     cap = B * H * W
     t = self.config.train
     sem, inst = self.in_sem, self.in_inst
-    labels = sem * self.div + inst                               # resnet_deeplab.py:112-117
-    ignore = labels.max() + 1
-    labels = torch.where(sem == self.ignore, ignore, labels)     # no .item() as masked_fill has
+    # resnet_deeplab.py:112-117 gives the dropped pixels the label `labels.max() + 1`; the value
+    # never leaves segment_by_kmeans (those pixels are removed, :355-365), so any label that
+    # cannot occur does: a constant saves the max-reduction in front of the clustering
+    ignore = 1 << 62
+    labels = torch.add(inst, sem, alpha=self.div).masked_fill_(sem == self.ignore, ignore)
     e, el, lab, cid, bid, img_off, count, _ = segsort_common.segment_core(
         self.in_emb, labels, self.num_clusters, None, self.in_loc, ignore, self.iterations,
         batch_index_offset=0)
