@@ -380,6 +380,13 @@ def run_b200(args):
         per_kernel[key] = r
     top = next(k for k in breakdown if k in per_kernel)
     roofline = dict(per_kernel[top])
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (a profiler
+    # number cannot be taken inside a timed run); null when this workload was not captured
+    tpath = os.path.join(ROOT, 'profiles', 'r1c_traffic.json')
+    if os.path.exists(tpath):
+      traffic = json.load(open(tpath))
+      roofline['traffic'] = traffic.get(w.name, {}).get(top)
+      roofline['traffic_source'] = traffic['source']
     roofline['shapes'] = shapes
     roofline['all'] = {k: {'bound': v['bound'], 'frac': v['frac'], 'ms_per_call': v['ms_per_call'],
                            'roofline_ms_per_call': v['roofline_ms_per_call']}
