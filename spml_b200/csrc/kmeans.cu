@@ -144,26 +144,22 @@ __device__ __forceinline__ void assign_tile(const KmeansArgs& p, const float* pr
 }
 
 
-// M-step accumulation for the tile.  The rows are first ranked by label (kmeans.cuh) so that a
-// warp sees long runs of one label whatever the spatial layout of the clusters; each warp
-// then walks 16 consecutive entries of that order with its lanes across the channels and
-// flushes a fixed-point run total whenever the label changes: about (labels in the tile + 8)
-// 64-bit reductions per channel and tile instead of one per label change along the raster.
+// M-step accumulation for the tile: each warp walks 16 consecutive rows with its lanes
+// across the channels and flushes a fixed-point run total whenever the label changes
+// (neighbouring pixels mostly share a cluster, so there are few atomics).
 __device__ __forceinline__ void accumulate_tile(const KmeansArgs& p, const Tile& tile,
                                                 const float* At, const int* s_lab,
-                                                const unsigned char* s_order,
                                                 long long* sums_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = BM / (kGemmThreads / 32);
-  const int e0 = warp * per, e1 = min(tile.rows, e0 + per);
+  const int r0 = warp * per, r1 = min(tile.rows, r0 + per);
   // a value is round(x * 2^32) kept as hi * 2^16 + lo with two exact 32-bit integers
   // (runs are at most 16 rows long, so neither half can overflow)
   int run_hi[kAccSlots], run_lo[kAccSlots];
 #pragma unroll
   for (int s = 0; s < kAccSlots; ++s) run_hi[s] = run_lo[s] = 0;
   int run_lab = -1;
-  for (int e = e0; e < e1; ++e) {
-    const int r = s_order[e];
+  for (int r = r0; r < r1; ++r) {
     const int lab = s_lab[r];
     if (lab != run_lab) {
       if (run_lab >= 0) {
@@ -209,8 +205,6 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
   float* At = smem;                       // [dpad][LDA]
   float* Bt = At + (size_t)p.dpad * LDA;  // [dpad][LDB]
   __shared__ int s_lab[BM];
-  __shared__ int s_rank[BM];
-  __shared__ unsigned char s_order[BM];
   __shared__ int s_last;
   const int tid = threadIdx.x;
   const int total_tiles = p.batch * p.tiles_per_img;
@@ -236,9 +230,10 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
       } else {
         // the prototypes of iteration it - 1 of THIS image (no grid-wide barrier)
         if (tid == 0) {
-          const unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
-          while (ld_acquire_gpu(flag) == 0) {
+          volatile unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
+          while (*flag == 0) {
           }
+          __threadfence();
         }
         __syncthreads();
         KM_TRACE(1);
@@ -251,8 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
       }
       if (it < p.iterations) {
         long long* sums_b = p.sums + (size_t)it * per_iter + b * per_img;
-        rank_rows_by_label(s_lab, tile.rows, s_rank, s_order);
-        accumulate_tile(p, tile, At, s_lab, s_order, sums_b);
+        accumulate_tile(p, tile, At, s_lab, sums_b);
         KM_TRACE(3);
         // publish: the CTA that adds the image's last tile normalises its prototypes
         __syncthreads();
@@ -260,18 +254,16 @@ __global__ void __launch_bounds__(kGemmThreads) kmeans_persistent_kernel(KmeansA
           const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
                                                      : p.rows_total);
           const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
-          fence_acq_rel_gpu();   // cumulative: the CTA's reductions (ordered by the barrier) first
+          __threadfence();
           s_last = atomicAdd(p.done + (size_t)it * p.batch + b, 1u) + 1 == tiles_b;
-          fence_acq_rel_gpu();
         }
         __syncthreads();
         if (s_last) {
+          __threadfence();
           finalize_prototypes(p, sums_b, kb, p.protos + (size_t)it * per_iter + b * per_img);
+          __threadfence();
           __syncthreads();
-          if (tid == 0) {
-            fence_acq_rel_gpu();   // cumulative over the CTA's stores (ordered by the barrier)
-            atomicExch(p.ready + (size_t)it * p.batch + b, 1u);
-          }
+          if (tid == 0) atomicExch(p.ready + (size_t)it * p.batch + b, 1u);
         }
         KM_TRACE(4);
       }

@@ -65,37 +65,6 @@ __device__ __forceinline__ void split_fixed(float v, int& hi, int& lo) {
 constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
 constexpr int kKmReplicas = 2;   // copies of the segment sums in the tensor-core path
 
-// __threadfence() compiles to MEMBAR.SC.GPU + CCTL.IVALL here; acquire / release is enough
-__device__ __forceinline__ void fence_acq_rel_gpu() {
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// s_order[i] = i-th row of the tile in (label, row) order.  All-pairs ranking: 128 x 128
-// compares over 256 threads.
-__device__ __forceinline__ void rank_rows_by_label(const int* s_lab, int rows, int* s_rank,
-                                                   unsigned char* s_order) {
-  const int tid = threadIdx.x;
-  if (tid < BM) s_rank[tid] = 0;
-  __syncthreads();
-  const int r = tid & (BM - 1), j0 = (tid >> 7) * (BM / 2);
-  const int mine = r < rows ? s_lab[r] : 0x7fffffff;
-  int cnt = 0;
-#pragma unroll 8
-  for (int j = j0; j < j0 + BM / 2; ++j) {
-    const int lj = j < rows ? s_lab[j] : 0x7fffffff;
-    cnt += (lj < mine) || (lj == mine && j < r);
-  }
-  atomicAdd(&s_rank[r], cnt);
-  __syncthreads();
-  if (tid < BM) s_order[s_rank[tid]] = (unsigned char)tid;
-  __syncthreads();
-}
-
 // kmeans_tc.cu
 bool kmeans_tc_supported(int dim);
 size_t kmeans_tc_split_bytes(int batch, int num_clusters, int dim, int iterations);
