@@ -41,3 +41,21 @@ def test_binding_table_names_exist_in_package():
   for mod, attrs in inst.BINDINGS.items():
     for name, repl in attrs.items():
       assert callable(repl), (mod, name)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'spml')), reason='reference not present')
+def test_run_launcher_executes_an_unchanged_script_with_rebound_symbols(tmp_path):
+  """python -m spml_b200.run SCRIPT: the script sees the rebound reference modules."""
+  import subprocess
+  script = tmp_path / 'probe.py'
+  script.write_text(
+      'import sys\n'
+      'import spml.utils.segsort.common as c, spml.utils.segsort.loss as l\n'
+      'print(c.segment_by_kmeans.__module__, l.SegSortLoss.__module__, sys.argv[1:])\n')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, REF]))
+  out = subprocess.run([sys.executable, '-m', 'spml_b200.run', '--spml-b200-lenient', str(script),
+                        '--flag', '7'], env=env, capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stderr
+  assert out.stdout.split()[:2] == ['spml_b200.segsort_common', 'spml_b200.segsort_loss']
+  assert "['--flag', '7']" in out.stdout
