@@ -14,7 +14,7 @@
 //               in TMEM (2 x 128 columns) so the epilogue of tile j overlaps the MMAs of j+1
 //   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns, ex2, code compare, running
 //               same / diff / self sums per row; two warps share each TMEM sub-partition
-//               (one per 64-column half)
+//               (forward: sixteen warps, one per 32-column quarter)
 #include <math.h>
 
 #include <stdlib.h>
@@ -183,8 +183,22 @@ __global__ void split_protos_kernel(const float* __restrict__ p, int64_t ld, int
 
 constexpr int kTcBM = 128;          // rows per CTA = UMMA M
 constexpr int kTcBN = 128;          // prototype columns per tile = UMMA N
-constexpr int kTcThreads = 320;     // producer + MMA + 8 epilogue warps
-constexpr int kTcEpiThreads = 256;
+// backward: producer + MMA + 16 epilogue warps (a warp owns 32 owner rows x 16 of the 64
+// streamed entities of a tile)
+// Warp 1 issues GEMM 1 (S), the LAST warp issues GEMM 2 (d(owner) += G . streamed): one
+// issuing thread spent ~1300 cycles per tile on the 16 MMAs plus ~900 on its four barrier
+// waits, more than the tensor pipe (~900) or the epilogue needed (SPML_TC_TRACE timeline).
+constexpr int kBwdEpiWarps = 16;
+constexpr int kBwdGemm2Warp = 2 + kBwdEpiWarps;
+constexpr int kTcThreads = (3 + kBwdEpiWarps) * 32;
+constexpr int kTcEpiThreads = kBwdEpiWarps * 32;
+constexpr int kBwdEpiCols = 64 / (kBwdEpiWarps / 4);   // S columns per epilogue warp
+// forward: producer + MMA + 16 epilogue warps.  The epilogue (exp, masks, row sums: ~10
+// instructions per similarity, MUFU-co-bound) is what bounds the kernel, and with 8 warps
+// there are 2 per scheduler: too few to cover the tcgen05.ld -> ex2 -> add chains.
+constexpr int kFwdEpiWarps = 16;
+constexpr int kFwdThreads = (2 + kFwdEpiWarps) * 32;
+constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
 constexpr int kKBlockBytesA = kTcBM * 128;  // one 64-wide K block of the A tile (bf16)
 constexpr int kKBlockBytesB = kTcBN * 128;
 
@@ -208,20 +222,20 @@ struct TcFwdArgs {
 };
 
 template <int kMode>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
                       const __grid_constant__ CUtensorMap map_el,
                       const __grid_constant__ CUtensorMap map_ph,
                       const __grid_constant__ CUtensorMap map_pl, const TcFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[2], bar_b_empty[2], bar_t_full[2],
+  __shared__ __align__(8) uint64_t bar_a_full, bar_b_full[4], bar_b_empty[4], bar_t_full[2],
       bar_t_empty[2];
   __shared__ uint32_t s_tmem_base;
   // prototype codes of the tiles in flight, written by warp 0.  The producer runs at most
   // `stages` tiles ahead of the MMA and an MMA only starts once every epilogue warp is
   // past the tile three before it, so a ring of stages + 3 <= 8 slots is never overrun.
   __shared__ __align__(16) int32_t s_ccode[8][kTcBN];
-  __shared__ float s_part[kTcBM][3];
+  __shared__ float s_part[3][kTcBM][3];   // partial sums of the column quarters 1..3
   __shared__ float s_nll[kTcBM];
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -249,11 +263,13 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
 
   if (warp == 0 && lane == 0) {
     tc::mbar_init(&bar_a_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       tc::mbar_init(&bar_b_full[s], 1);
       tc::mbar_init(&bar_b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bar_t_full[s], 1);
-      tc::mbar_init(&bar_t_empty[s], kTcEpiThreads / 32);
+      tc::mbar_init(&bar_t_empty[s], kFwdEpiWarps);
     }
     tc::fence_barrier_init();
     tc::prefetch_tensormap(&map_eh);
@@ -280,12 +296,19 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
     }
     for (int j = 0; j < ntiles; ++j) {
       const int s = j % a.stages, use = j / a.stages;
-      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
       const int32_t c0 = c_begin + j * kTcBN;
-      // the tile's prototype codes ride along with the stage (ordered before lane 0's
-      // arrive by __syncwarp, seen by the epilogue through b_full -> MMA -> t_full)
-      for (int k = lane; k < kTcBN; k += 32)
-        s_ccode[j & 7][k] = c0 + k < c_end ? a.ccode[c0 + k] : 0;
+      // the tile's prototype codes do not depend on the ring slot: fetch them before the wait
+      int code4[kTcBN / 32];
+#pragma unroll
+      for (int h = 0; h < kTcBN / 32; ++h) {
+        const int k = lane + 32 * h;
+        code4[h] = c0 + k < c_end ? a.ccode[c0 + k] : 0;
+      }
+      tc::mbar_wait(&bar_b_empty[s], (use & 1) ^ 1);      // every lane: the stage is free
+      // they ride along with the stage (ordered before lane 0's arrive by __syncwarp, seen by
+      // the epilogue through b_full -> MMA -> t_full)
+#pragma unroll
+      for (int h = 0; h < kTcBN / 32; ++h) s_ccode[j & 7][lane + 32 * h] = code4[h];
       __syncwarp();
       if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_b_full[s], stage_bytes);
@@ -344,12 +367,13 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
   } else {
     // ===================================================================== epilogue
     const int sp = warp & 3;                  // TMEM sub-partition of this warp
-    const int half = (warp - 2) >> 2;         // which 64-column half of the tile
+    const int quarter = (warp - 2) >> 2;      // which 32-column quarter of the tile
     const int row = sp * 32 + lane;
     const bool row_ok = row < rows;
     const int code_i = row_ok ? a.rcode[row0 + row] : 0;
     const int seg_i = row_ok ? a.rseg[row0 + row] : -1;
     float same = 0.f, diff = 0.f, self = 0.f;
+    const int cb = quarter * 32;
 
     for (int j = 0; j < ntiles; ++j) {
       const int acc = j & 1, ause = j >> 1, st = j & 7;
@@ -357,48 +381,45 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
       const bool tail = c0 + kTcBN > c_end;          // only the last tile has dead columns
-      const int seg_rel = seg_i - c0 - half * 64;    // own segment relative to this half
+      const int seg_rel = seg_i - c0 - cb;           // own segment relative to this quarter
+      uint32_t v[32], w[32];
+      const uint32_t taddr = tmem_base + acc * 2 * kTcBN + cb + (static_cast<uint32_t>(sp * 32) << 16);
+      tc::tmem_ld_32x32(taddr, v);             // hi.hi + lo.hi
+      tc::tmem_ld_32x32(taddr + kTcBN, w);     // hi.lo
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();              // the loads are done: hand the accumulator back
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
+      const int4* codes = reinterpret_cast<const int4*>(&s_ccode[st][cb]);
 #pragma unroll
-      for (int chunk = 0; chunk < 2; ++chunk) {
-        const int cb = half * 64 + chunk * 32;
-        uint32_t v[32], w[32];
-        const uint32_t taddr = tmem_base + acc * 2 * kTcBN + cb + (static_cast<uint32_t>(sp * 32) << 16);
-        tc::tmem_ld_32x32(taddr, v);             // hi.hi + lo.hi
-        tc::tmem_ld_32x32(taddr + kTcBN, w);     // hi.lo
-        tc::tmem_ld_wait();
-        if (chunk == 1) {  // both loads of this warp are done: hand the accumulator back
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bar_t_empty[acc]);
-        }
-        const int4* codes = reinterpret_cast<const int4*>(&s_ccode[st][cb]);
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const int4 c4 = codes[q4];
+        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const int4 c4 = codes[q4];
-          const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int q = q4 * 4 + u;
-            float s = tc::fast_exp2((__uint_as_float(v[q]) + __uint_as_float(w[q])) * a.kappa_log2e);
-            if (tail) s = c0 + cb + q < c_end ? s : 0.f;
-            const bool match = kMode == SPML_MODE_TAGS ? (code_i & cc[u]) != 0 : code_i == cc[u];
-            if (match) same += s; else diff += s;
-            if (chunk * 32 + q == seg_rel) self += s;
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int q = q4 * 4 + u;
+          float s = tc::fast_exp2((__uint_as_float(v[q]) + __uint_as_float(w[q])) * a.kappa_log2e);
+          if (tail) s = c0 + cb + q < c_end ? s : 0.f;
+          const bool match = kMode == SPML_MODE_TAGS ? (code_i & cc[u]) != 0 : code_i == cc[u];
+          if (match) same += s; else diff += s;
+          if (q == seg_rel) self += s;
         }
       }
     }
-    // the two column halves of a row live in different warps: combine in a fixed order
-    if (half == 1) {
-      s_part[row][0] = same;
-      s_part[row][1] = diff;
-      s_part[row][2] = self;
+    // the four column quarters of a row live in different warps: combine in a fixed order
+    if (quarter > 0) {
+      s_part[quarter - 1][row][0] = same;
+      s_part[quarter - 1][row][1] = diff;
+      s_part[quarter - 1][row][2] = self;
     }
-    tc::named_bar_sync(1, kTcEpiThreads);
-    if (half == 0) {
-      same += s_part[row][0];
-      diff += s_part[row][1];
-      self += s_part[row][2];
+    tc::named_bar_sync(1, kFwdEpiThreads);
+    if (quarter == 0) {
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq) {
+        same += s_part[qq][row][0];
+        diff += s_part[qq][row][1];
+        self += s_part[qq][row][2];
+      }
       float nll = 0.f;
       if (row_ok) {
         const float others = same - self;   // loss.py:64-70
@@ -414,7 +435,7 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
       }
       s_nll[row] = nll;
     }
-    tc::named_bar_sync(1, kTcEpiThreads);
+    tc::named_bar_sync(1, kFwdEpiThreads);
     if (warp == 2) {
       float v = s_nll[lane] + s_nll[lane + 32] + s_nll[lane + 64] + s_nll[lane + 96];
       v = warp_sum(v);
@@ -450,7 +471,6 @@ constexpr int kBwdTileBytesA = kBwdBM * 128;   // one 64-wide K block of the own
 constexpr int kBwdTileBytesB = kBwdBN * 128;   // one 64-wide block of the streamed tile
 constexpr int kBwdGBytes = kBwdBM * 128;       // G tile, 128 x 64 bf16
 constexpr int kBwdMaxStages = 4;
-constexpr int kBwdGTmemCol = 384;   // TMEM columns [384, 512): two G buffers of (32 hi + 32 lo)
 
 #ifdef SPML_TC_TRACE
 #define SPML_TRACE(slot)                                                              \
@@ -482,7 +502,6 @@ struct TcBwdArgs {
   int nkb, ksteps, stages;
   int n2;                     // GEMM 2 N: dim rounded up to 16
   int tmem_cols;
-  int g_in_tmem;              // G tile handed to GEMM 2 through TMEM (TS MMA) instead of smem
   int stacked;                // nkb == 1: hi/lo streamed tiles read as one operand (2 MMAs per K step)
 };
 
@@ -581,7 +600,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
   const int owned = (int)min((int64_t)kBwdBM, o_end - o0);
   if (s_lo >= s_hi) {
     // nothing streams past this tile: dP partials are pre-zeroed, dE rows are written here
-    if (!kProtoOwner && warp >= 2 && (warp - 2) < 4) {
+    if (!kProtoOwner && warp >= 2 && (warp - 2) < 4) {   // one warp per 32 owner rows
       const int row = (warp - 2) * 32 + lane;
       if (row < owned) {
         const int64_t orow = o0 + row;
@@ -692,21 +711,16 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+    // ===================================================================== GEMM 1 issuer
     // the whole warp runs the loop (uniform control flow and operands); one elected lane
     // issues the MMAs and commits
     {
       constexpr uint32_t idesc1 = tc::umma_idesc_bf16(kBwdBM, kBwdBN, 0, 0);
       constexpr uint32_t idesc1s = tc::umma_idesc_bf16(kBwdBM, 2 * kBwdBN, 0, 0);
-      const uint32_t idesc2 = tc::umma_idesc_bf16(kBwdBM, a.n2, 0, 1);
-      const uint32_t idesc2s = tc::umma_idesc_bf16(kBwdBM, 64 + a.n2, 0, 1);
       const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
       const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
       const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
       const uint32_t ring_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), 16);
-      // GEMM 2 operands: G tile K-major; streamed tile MN-major with LBO = next 64-wide N atom
-      const uint32_t g_lo = tc::umma_desc_lo(tc::smem_u32(g_ring), 16);
-      const uint32_t ring_mn_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), kBwdTileBytesB);
       auto gemm1 = [&](int j) {
         const int s = j % a.stages, use = j / a.stages;
         const int acc = j & 1, ause = j >> 1;
@@ -751,14 +765,22 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         SPML_TRACE(11);
       };
       tc::mbar_wait(&bar_a_full, 0);
-      gemm1(0);
+      for (int j = 0; j < ntiles; ++j) gemm1(j);   // the ring and t_empty barriers pace it
+    }
+  } else if (warp == kBwdGemm2Warp) {
+    // ===================================================================== GEMM 2 issuer
+    {
+      const uint32_t idesc2 = tc::umma_idesc_bf16(kBwdBM, a.n2, 0, 1);
+      const uint32_t idesc2s = tc::umma_idesc_bf16(kBwdBM, 64 + a.n2, 0, 1);
+      const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
+      // G tile K-major; streamed tile MN-major with LBO = next 64-wide N atom
+      const uint32_t g_lo = tc::umma_desc_lo(tc::smem_u32(g_ring), 16);
+      const uint32_t ring_mn_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), kBwdTileBytesB);
       for (int j = 0; j < ntiles; ++j) {
-        if (a.stages >= 2 && j + 1 < ntiles) gemm1(j + 1);
-        const int s = j % a.stages, gb = j & 1, guse = j >> 1;
-        SPML_TRACE(12);
+        const int s = j % a.stages, use = j / a.stages, gb = j & 1, guse = j >> 1;
+        tc::mbar_wait(&bar_b_full[s], use & 1);     // this thread reads the streamed tile too
         tc::mbar_wait(&bar_g_full[gb], guse & 1);
         tc::tcgen05_fence_after();
-        SPML_TRACE(13);
         uint32_t bh = ring_mn_lo + s * (stage_bytes >> 4);
         uint32_t bl = bh + a.nkb * (kBwdTileBytesB >> 4);
         uint32_t accumulate = j > 0 ? 1u : 0u;
@@ -766,32 +788,12 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         if (a.stacked) {
           // MN-major B: the next 64-wide N atom (LBO) of the hi tile IS the lo tile, so
           // G_hi x [P_hi | P_lo] is one MMA of N = 64 + n2; G_lo x P_hi adds to block 0
-          if (a.g_in_tmem) {
-            uint32_t gh = tmem_base + kBwdGTmemCol + gb * 64, gl = gh + 32;
-            for (int ks = 0; ks < kBwdBN / 16; ++ks) {
-              tc::umma_bf16_ts_words(tmem_acc, gh, bh, hi_k, idesc2s, accumulate);
-              tc::umma_bf16_ts_words(tmem_acc, gl, bh, hi_k, idesc2, 1);
-              accumulate = 1;
-              gh += 8, gl += 8, bh += 128;
-            }
-          } else {
-            uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
-            for (int ks = 0; ks < kBwdBN / 16; ++ks) {
-              tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2s, accumulate);
-              tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
-              accumulate = 1;
-              gh += 2, gl += 2, bh += 128;
-            }
-          }
-        } else if (a.g_in_tmem) {
-          // A = G straight from TMEM: 16 columns of G = 8 packed 32-bit TMEM columns
-          uint32_t gh = tmem_base + kBwdGTmemCol + gb * 64, gl = gh + 32;
+          uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
           for (int ks = 0; ks < kBwdBN / 16; ++ks) {
-            tc::umma_bf16_ts_words(tmem_acc, gh, bh, hi_k, idesc2, accumulate);
-            tc::umma_bf16_ts_words(tmem_acc, gl, bh, hi_k, idesc2, 1);
-            tc::umma_bf16_ts_words(tmem_acc, gh, bl, hi_k, idesc2, 1);
+            tc::umma_bf16_words(tmem_acc, gh, hi_k, bh, hi_k, idesc2s, accumulate);
+            tc::umma_bf16_words(tmem_acc, gl, hi_k, bh, hi_k, idesc2, 1);
             accumulate = 1;
-            gh += 8, gl += 8, bh += 128, bl += 128;
+            gh += 2, gl += 2, bh += 128;
           }
         } else {
           uint32_t gh = g_lo + gb * (2 * kBwdGBytes >> 4), gl = gh + (kBwdGBytes >> 4);
@@ -804,19 +806,18 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
             gh += 2, gl += 2, bh += 128, bl += 128;
           }
         }
+        // GEMM 1 of this tile completed before its G existed: the slot is free after GEMM 2
         tc::umma_commit(&bar_b_empty[s]);
         tc::umma_commit(&bar_g_empty[gb]);
         if (j + 1 == ntiles) tc::umma_commit(&bar_d_full);
         }
         __syncwarp();
-        SPML_TRACE(14);
-        if (a.stages == 1 && j + 1 < ntiles) gemm1(j + 1);
       }
     }
   } else {
     // ===================================================================== epilogue
     const int sp = warp & 3;
-    const int half = (warp - 2) >> 2;          // 32-column half of the 64-wide S tile
+    const int quarter = (warp - 2) >> 2;       // 16-column quarter of the 64-wide S tile
     const int row = sp * 32 + lane;            // owner entity of this thread
     const bool row_ok = row < owned;
     const int64_t orow = o0 + row;
@@ -828,7 +829,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         code_o = a.rcode[orow];
         seg_o = a.rseg[orow];
         pm_o = load_pix_meta(a, orow, weight);
-        if (half == 0 && a.pm) a.pm[orow] = make_float4(pm_o.w00, pm_o.w10, pm_o.w01, pm_o.w11);
+        if (quarter == 0 && a.pm) a.pm[orow] = make_float4(pm_o.w00, pm_o.w10, pm_o.w01, pm_o.w11);
       } else {
         code_o = a.ccode[orow];
       }
@@ -843,16 +844,17 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       tc::mbar_wait(&bar_t_full[acc], ause & 1);
       tc::tcgen05_fence_after();
       SPML_TRACE(1);
-      uint32_t v[32];
-      const int cb = half * 32;
+      uint32_t v[kBwdEpiCols];
+      const int cb = quarter * kBwdEpiCols;
       const uint32_t s_addr = tmem_base + acc * s_stride + cb + (static_cast<uint32_t>(sp * 32) << 16);
-      tc::tmem_ld_32x32(s_addr, v);
+      tc::tmem_ld_32x16(s_addr, v);
       if (a.stacked) {
-        uint32_t w[32];
-        tc::tmem_ld_32x32(s_addr + kBwdBN, w);   // the hi.lo block
+        uint32_t w[kBwdEpiCols];
+        tc::tmem_ld_32x16(s_addr + kBwdBN, w);   // the hi.lo block
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+        for (int q = 0; q < kBwdEpiCols; ++q)
+          v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
       } else {
         tc::tmem_ld_wait();
       }
@@ -869,7 +871,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       int own_rel = 0;
       if (!kProtoOwner) {
         own_rel = seg_o - (int)s0 - cb;   // column of this pixel's own prototype
-        any_own = __any_sync(0xffffffffu, static_cast<unsigned>(own_rel) < 32u);
+        any_own = __any_sync(0xffffffffu, static_cast<unsigned>(own_rel) < (unsigned)kBwdEpiCols);
       } else {
         // pixels of the streamed tile own prototypes in [segmin, segmax] only
         const int r_lo = (int)o0 + sp * 32;
@@ -877,7 +879,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       }
       if (!any_own) {
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
+        for (int q4 = 0; q4 < kBwdEpiCols / 4; ++q4) {
           const int4 cc = *reinterpret_cast<const int4*>(&s_code[st][cb + q4 * 4]);
           const int c4[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
@@ -897,7 +899,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
+        for (int q = 0; q < kBwdEpiCols; ++q) {
           const int k = cb + q;
           const float z = __uint_as_float(v[q]);
           float gq;
@@ -912,35 +914,20 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       }
       if (kProtoOwner && !row_ok) {   // padding prototypes of the last owner tile
 #pragma unroll                        // (padding PIXEL rows have all-zero weights instead)
-        for (int q = 0; q < 32; ++q) v[q] = 0u;
+        for (int q = 0; q < kBwdEpiCols; ++q) v[q] = 0u;
       }
       if (s0 + kBwdBN > s_hi) {       // last streamed tile: columns past the end
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = s0 + cb + q < s_hi ? v[q] : 0u;
+        for (int q = 0; q < kBwdEpiCols; ++q) v[q] = s0 + cb + q < s_hi ? v[q] : 0u;
       }
       SPML_TRACE(2);
       tc::mbar_wait(&bar_g_empty[gb], (guse & 1) ^ 1);
       SPML_TRACE(3);
-      if (a.g_in_tmem) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float x = __uint_as_float(v[2 * c]), y = __uint_as_float(v[2 * c + 1]);
-          const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
-          hi[c] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
-          lo[c] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
-        }
-        const uint32_t taddr = tmem_base + kBwdGTmemCol + gb * 64 + (cb >> 1) +
-                               (static_cast<uint32_t>(sp * 32) << 16);
-        tc::tmem_st_32x16(taddr, hi);
-        tc::tmem_st_32x16(taddr + 32, lo);
-        tc::tmem_st_wait();
-        tc::tcgen05_fence_before();
-      } else {
+      {
         uint8_t* gh = g_ring + (size_t)gb * 2 * kBwdGBytes;
         uint8_t* gl = gh + kBwdGBytes;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < kBwdEpiCols / 8; ++c4) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p2 = 0; p2 < 4; ++p2) {
@@ -949,7 +936,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
             hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
             lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
           }
-          const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4);
+          const uint32_t chunk = static_cast<uint32_t>(quarter * (kBwdEpiCols / 8) + c4);
           const uint32_t off = g_row_off + ((chunk ^ sw) << 4);
           *reinterpret_cast<uint4*>(gh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(gl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -976,7 +963,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       }
     }
     const int nchunks = (a.n2 + 31) / 32;
-    for (int ch = half; ch < nchunks; ch += 2) {
+    for (int ch = quarter; ch < nchunks; ch += kBwdEpiWarps / 4) {
       uint32_t v[32];
       const uint32_t d_addr = tmem_acc + ch * 32 + (static_cast<uint32_t>(sp * 32) << 16);
       tc::tmem_ld_32x32(d_addr, v);
@@ -1029,7 +1016,7 @@ TcPlan segsort_tc_plan(const spml_segsort_desc& d, void* base) {
   p.dp = (d.dim + 7) & ~7;
   p.nkb = (d.dim + 63) / 64;
   p.ksteps = (d.dim + 15) / 16;
-  p.stages = p.nkb <= 2 ? 2 : 1;
+  p.stages = p.nkb == 1 ? 4 : (p.nkb == 2 ? 2 : 1);   // forward ring: what fits next to the A tile
   char* ptr = reinterpret_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -1111,12 +1098,12 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
     SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel<SPML_MODE_TAGS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     segsort_fwd_tc_kernel<SPML_MODE_TAGS>
-        <<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+        <<<grid, kFwdThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
   } else {
     SPML_CUDA(cudaFuncSetAttribute(segsort_fwd_tc_kernel<SPML_MODE_CLASS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     segsort_fwd_tc_kernel<SPML_MODE_CLASS>
-        <<<grid, kTcThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
+        <<<grid, kFwdThreads, smem, st>>>(map_eh, map_el, map_ph, map_pl, a);
   }
   SPML_LAUNCH_CHECK("segsort_fwd_tc_kernel");
   return SPML_OK;
@@ -1158,22 +1145,16 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.ksteps = p.ksteps;
   a.stages = p.nkb == 1 ? 4 : (p.nkb == 2 ? 2 : 1);   // what fits next to the A and G tiles
   a.n2 = (d.dim + 15) & ~15;
-  static int ts_mode = -1;
-  if (ts_mode < 0) {
-    const char* e = getenv("SPML_B200_G_TMEM");
-    ts_mode = e ? atoi(e) : 0;
-  }
   static int stack_mode = -1;
   if (stack_mode < 0) {
     const char* e = getenv("SPML_B200_STACK");
     stack_mode = e ? atoi(e) : 1;
   }
   a.stacked = stack_mode && p.nkb == 1;
-  // TMEM columns: S buffers | d(owner) | (G buffers at kBwdGTmemCol)
+  // TMEM columns: S buffers | d(owner)
   const int s_cols = a.stacked ? 4 * kBwdBN : 2 * kBwdBN;
   const int d_cols = a.stacked ? 64 + a.n2 : a.n2;
-  a.g_in_tmem = ts_mode && (s_cols + d_cols <= kBwdGTmemCol);
-  a.tmem_cols = a.g_in_tmem ? 512 : (s_cols + d_cols <= 256 ? 256 : 512);
+  a.tmem_cols = s_cols + d_cols <= 256 ? 256 : 512;
   const size_t smem = 1024 + (size_t)2 * p.nkb * kBwdTileBytesA +
                       (size_t)a.stages * 2 * p.nkb * kBwdTileBytesB + (size_t)4 * kBwdGBytes;
   if (smem > 227 * 1024) {
