@@ -117,9 +117,13 @@ __device__ __forceinline__ void split_store(float x, float y, __nv_bfloat16* hi,
   *reinterpret_cast<__nv_bfloat162*>(lo + at) = __halves2bfloat162(xl, yl);
 }
 
-// one warp per problem row: gather, split into bf16 hi / lo (zero padded to dp columns),
-// narrow the labels to int32 and translate the segment id to a compact column.
+// one warp per problem row: gather, scale, split into bf16 hi / lo (zero padded to dp
+// columns), narrow the labels to int32 and translate the segment id to a compact column.
+// `scale` = kappa * log2(e): the similarity GEMM then delivers the exponent of exp2
+// directly (one multiply less per similarity in every epilogue); the kernel that
+// re-uses the pixel rows as the second GEMM's operand folds 1 / scale into its weights.
 __global__ void split_rows_kernel(const float* __restrict__ x, int64_t ld, int dim, int dp,
+                                  float scale,
                                   const int32_t* __restrict__ row_index,
                                   const int32_t* __restrict__ group_off, int num_groups,
                                   int64_t n_rows, const int64_t* __restrict__ pix_code,
@@ -141,8 +145,8 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int64_t ld, int d
   const int64_t orig = row_index ? (int64_t)row_index[r] : r;
   const float* xr = x + orig * ld;
   for (int q = lane * 2; q < dp; q += 64) {
-    const float a = q < dim ? xr[q] : 0.f;
-    const float b = q + 1 < dim ? xr[q + 1] : 0.f;
+    const float a = q < dim ? xr[q] * scale : 0.f;
+    const float b = q + 1 < dim ? xr[q + 1] * scale : 0.f;
     split_store(a, b, hi, lo, r * dp + q);
   }
   if (lane == 0) {
@@ -214,7 +218,6 @@ struct TcFwdArgs {
   float* stats;
   float* nll;
   float* partial;
-  float kappa_log2e;
   int mode;
   int nkb;       // 64-wide K blocks
   int ksteps;    // 16-wide K steps
@@ -398,12 +401,18 @@ segsort_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_eh,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int q = q4 * 4 + u;
-          float s = tc::fast_exp2((__uint_as_float(v[q]) + __uint_as_float(w[q])) * a.kappa_log2e);
+          float s = tc::fast_exp2(__uint_as_float(v[q]) + __uint_as_float(w[q]));
           if (tail) s = c0 + cb + q < c_end ? s : 0.f;
           const bool match = kMode == SPML_MODE_TAGS ? (code_i & cc[u]) != 0 : code_i == cc[u];
           if (match) same += s; else diff += s;
-          if (q == seg_rel) self += s;
+          v[q] = __float_as_uint(s);
         }
+      }
+      // a pixel's own segment is ONE column of the bank: only the warps that hold it look
+      if (__any_sync(0xffffffffu, static_cast<unsigned>(seg_rel) < 32u)) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (q == seg_rel) self += __uint_as_float(v[q]);
       }
     }
     // the four column quarters of a row live in different warps: combine in a fixed order
@@ -498,7 +507,7 @@ struct TcBwdArgs {
   float* out;                 // demb, or the [chunks][m][dim] prototype partials
   int64_t ld_out;
   float beta;
-  float kappa_log2e;
+  float inv_scale;            // 1 / (kappa log2 e): the pixel operand rows are pre-scaled
   int nkb, ksteps, stages;
   int n2;                     // GEMM 2 N: dim rounded up to 16
   int tmem_cols;
@@ -535,13 +544,14 @@ __global__ void pix_meta_kernel(const TcBwdArgs a) {
   const int64_t r = r_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= r_end) return;
   const PixMeta pm = load_pix_meta(a, r, reduction_weight(d, g));
-  a.pm[r] = make_float4(pm.w00, pm.w10, pm.w01, pm.w11);
+  const float u = a.inv_scale;
+  a.pm[r] = make_float4(pm.w00 * u, pm.w10 * u, pm.w01 * u, pm.w11 * u);
 }
 
 template <int kMode>
-__device__ __forceinline__ float grad_elem(float z, float kl2e, int code_pix, int code_pro,
+__device__ __forceinline__ float grad_elem(float z, int code_pix, int code_pro,
                                            bool own, const PixMeta& pm) {
-  const float s = tc::fast_exp2(z * kl2e);
+  const float s = tc::fast_exp2(z);
   const bool match = kMode == SPML_MODE_TAGS ? (code_pix & code_pro) != 0 : code_pix == code_pro;
   const float w_own = match ? pm.w11 : pm.w01;
   const float w_oth = match ? pm.w10 : pm.w00;
@@ -829,7 +839,10 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         code_o = a.rcode[orow];
         seg_o = a.rseg[orow];
         pm_o = load_pix_meta(a, orow, weight);
-        if (quarter == 0 && a.pm) a.pm[orow] = make_float4(pm_o.w00, pm_o.w10, pm_o.w01, pm_o.w11);
+        if (quarter == 0 && a.pm) {   // for the prototype-owner kernel: its second GEMM multiplies
+          const float u = a.inv_scale;   // G with the SCALED pixel rows
+          a.pm[orow] = make_float4(pm_o.w00 * u, pm_o.w10 * u, pm_o.w01 * u, pm_o.w11 * u);
+        }
       } else {
         code_o = a.ccode[orow];
       }
@@ -866,7 +879,6 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       // holds for one column per pixel, so almost every (warp, tile) pair takes the lean loop
       // that only applies the match weights: the epilogue is instruction-issue-bound (the
       // tensor pipe needs ~900 cycles per step, this loop was ~2400 with the own selects in).
-      const float kl = a.kappa_log2e;
       bool any_own;
       int own_rel = 0;
       if (!kProtoOwner) {
@@ -885,7 +897,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int q = q4 * 4 + r;
-            const float e = tc::fast_exp2(__uint_as_float(v[q]) * kl);
+            const float e = tc::fast_exp2(__uint_as_float(v[q]));
             const bool match = kMode == SPML_MODE_TAGS ? (code_o & c4[r]) != 0 : code_o == c4[r];
             float w;
             if (!kProtoOwner) {
@@ -904,9 +916,9 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
           const float z = __uint_as_float(v[q]);
           float gq;
           if (!kProtoOwner) {
-            gq = grad_elem<kMode>(z, kl, code_o, s_code[st][k], q == own_rel, pm_o);
+            gq = grad_elem<kMode>(z, code_o, s_code[st][k], q == own_rel, pm_o);
           } else {
-            gq = grad_elem<kMode>(z, kl, s_code[st][k], code_o, s_seg[st][k] == (int)orow,
+            gq = grad_elem<kMode>(z, s_code[st][k], code_o, s_seg[st][k] == (int)orow,
                                   s_pm[st][k]);
           }
           v[q] = __float_as_uint(gq);
@@ -931,10 +943,12 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p2 = 0; p2 < 4; ++p2) {
-            const float x = __uint_as_float(v[c4 * 8 + p2 * 2]), y = __uint_as_float(v[c4 * 8 + p2 * 2 + 1]);
-            const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
-            hi[p2] = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
-            lo[p2] = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
+            // hi = the top 16 bits (truncation: one byte-permute packs both), lo = the exact
+            // remainder rounded to bf16: the pair still carries ~16 mantissa bits
+            const uint32_t xb = v[c4 * 8 + p2 * 2], yb = v[c4 * 8 + p2 * 2 + 1];
+            hi[p2] = __byte_perm(xb, yb, 0x7632);
+            lo[p2] = pack_bf16x2(__uint_as_float(xb) - __uint_as_float(xb & 0xffff0000u),
+                                 __uint_as_float(yb) - __uint_as_float(yb & 0xffff0000u));
           }
           const uint32_t chunk = static_cast<uint32_t>(quarter * (kBwdEpiCols / 8) + c4);
           const uint32_t off = g_row_off + ((chunk ^ sw) << 4);
@@ -1049,7 +1063,7 @@ int segsort_tc_prepare(const spml_segsort_desc& d, const TcPlan& p, cudaStream_t
     SPML_LAUNCH_CHECK("compact_cols_kernel");
   }
   split_rows_kernel<<<(unsigned)ceil_div(d.n_rows, 8), 256, 0, st>>>(
-      d.emb, d.ld_emb, d.dim, p.dp, d.row_index, d.group_off, d.num_groups, d.n_rows, d.pix_code,
+      d.emb, d.ld_emb, d.dim, p.dp, (float)((double)d.kappa * 1.4426950408889634), d.row_index, d.group_off, d.num_groups, d.n_rows, d.pix_code,
       d.seg, compact ? p.col_dst : nullptr, d.m, p.eh, p.el, p.rcode, p.rseg);
   SPML_LAUNCH_CHECK("split_rows_kernel");
   split_protos_kernel<<<(unsigned)ceil_div(d.m, 8), 256, 0, st>>>(
@@ -1082,7 +1096,6 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
   a.stats = stats;
   a.nll = nll;
   a.partial = p.partial;
-  a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
   a.mode = d.mode;
   a.nkb = p.nkb;
   a.ksteps = p.ksteps;
@@ -1140,7 +1153,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.stats = stats;
   a.grad_loss = grad_loss;
   a.pm = p.pm;
-  a.kappa_log2e = (float)((double)d.kappa * 1.4426950408889634);
+  a.inv_scale = (float)(1.0 / ((double)d.kappa * 1.4426950408889634));
   a.nkb = p.nkb;
   a.ksteps = p.ksteps;
   a.stages = p.nkb == 1 ? 4 : (p.nkb == 2 ? 2 : 1);   // what fits next to the A and G tiles
