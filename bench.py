@@ -236,9 +236,19 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
-    # keep stdout for the one JSON line: NCCL's version / debug lines go to stderr
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-    dist.init_process_group('nccl', device_id=dev)
+    # keep stdout for the one JSON line: NCCL prints its version (and any NCCL_DEBUG output)
+    # on stdout when the communicator is created, so fd 1 points at stderr until then
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      dist.init_process_group('nccl', device_id=dev)
+      dist.barrier()
+      torch.cuda.synchronize()
+    finally:
+      sys.stdout.flush()
+      os.dup2(saved, 1)
+      os.close(saved)
   _lib.load()
 
   w = synth.WORKLOADS[args.workload]
