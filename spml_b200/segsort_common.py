@@ -153,11 +153,12 @@ def _compress_seed_maps(cluster_indices, batch, n):
 
 
 def segment_core(embeddings, labels, num_clusters, cluster_indices, local_features,
-                 ignore_index, iterations, batch_index_offset=None):
+                 ignore_index, iterations, batch_index_offset=None, after_pack=None):
   """Everything of segment_by_kmeans up to (not including) the host read-back.  Returns
   fixed-CAPACITY tensors (batch * H * W rows; rows past the live count are padding) and
   device-side counts: (e, el, labels, segment_ids, batch_ids, img_off int32 [B+1],
-  num_segments int32 [1])."""
+  num_segments int32 [1]).  `after_pack(batch_ids)` is called between the packing and the
+  clustering launch (the fixed-capacity head forks side-stream work there)."""
   if embeddings.dim() != 4:
     raise ValueError('embeddings must be [batch, channels, height, width]')
   if not embeddings.is_cuda:
@@ -186,6 +187,8 @@ def segment_core(embeddings, labels, num_clusters, cluster_indices, local_featur
     batch_index_offset = B * (dev.index or 0)                           # :376-377
   e, el, lab, bid, seed = ops.NormalizePack.apply(
       embeddings, local_features, labels_c, seeds, dst, batch_index_offset)
+  if after_pack is not None:     # work that only needs the batch ids can overlap the clustering
+    after_pack(bid)
   _, km = ops.kmeans(el.detach(), img_off, B, n, num_k, iterations, seed, k_per_image)
   # :398-405: rank of (image, cluster, label) among the triples that occur
   inverse, _, _, count, _ = ops.unique_inverse(lab, hi=bid * num_k + km, bound=0,

@@ -79,7 +79,7 @@ class StaticContrastiveHead(nn.Module):
     self.bank_mask = z(S, M, dtype=torch.int64)
     self.bank_live = z(S, M, dtype=torch.uint8)
     self.out = {}
-    self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
 
   # ------------------------------------------------------------------------------ one step
   def _forward(self):
@@ -92,18 +92,36 @@ class StaticContrastiveHead(nn.Module):
     # cannot occur does: a constant saves the max-reduction in front of the clustering
     ignore = 1 << 62
     labels = torch.add(inst, sem, alpha=self.div).masked_fill_(sem == self.ignore, ignore)
+    main = torch.cuda.current_stream(dev)
+    streams = self._side_streams
+    side = {}
+
+    def tag_masks(bid):
+      # image-tag masks per pixel (segsort.py:146-150): they only need the batch ids, so they
+      # run on a side stream next to the clustering kernel
+      ev = torch.cuda.Event()
+      ev.record(main)
+      with torch.cuda.stream(streams[0]):
+        streams[0].wait_event(ev)
+        side['img_masks'] = ops.pack_tags(self.in_tags[:, 1:C])
+        side['pix_mask'] = torch.index_select(side['img_masks'], 0, bid)
+
     e, el, lab, cid, bid, img_off, count, _ = segsort_common.segment_core(
         self.in_emb, labels, self.num_clusters, None, self.in_loc, ignore, self.iterations,
-        batch_index_offset=0)
+        batch_index_offset=0, after_pack=tag_masks)
     n_dev = img_off[B:B + 1]
     sem_pix, inst_pix, keep, p_sem, p_inst, p_bid, p_live = ops.segment_labels(
         lab, bid, cid, n_dev, self.div, C, self.m_cap, C, self.overflow)
-    protos = ops.SegmentPrototypes.apply(e, cid, self.m_cap, n_dev)          # models/utils.py:113
-    protos_loc = ops.SegmentPrototypes.apply(el, cid, self.m_cap, n_dev)
-
-    # image-tag masks (segsort.py:146-150) per pixel and per prototype
-    img_masks = ops.pack_tags(self.in_tags[:, 1:C])
-    pix_mask = torch.index_select(img_masks, 0, bid)
+    # the two prototype sets (models/utils.py:113-116) are independent: one per stream
+    ev = torch.cuda.Event()
+    ev.record(main)
+    with torch.cuda.stream(streams[1]):
+      streams[1].wait_event(ev)
+      protos_loc = ops.SegmentPrototypes.apply(el, cid, self.m_cap, n_dev)
+    protos = ops.SegmentPrototypes.apply(e, cid, self.m_cap, n_dev)
+    main.wait_stream(streams[0])
+    main.wait_stream(streams[1])
+    img_masks, pix_mask = side['img_masks'], side['pix_mask']
     cur_mask = torch.index_select(img_masks, 0, p_bid.clamp(min=0))
     use_bank = self.bank_size > 0
     if use_bank:                                                             # :153-182
@@ -113,16 +131,26 @@ class StaticContrastiveHead(nn.Module):
       plive_all = torch.cat([p_live, self.bank_live.view(-1)], 0)
     else:
       p_all, psem_all, pmask_all, plive_all = protos, p_sem, cur_mask, p_live
+    if use_bank:
+      # train.py:276-293.  The concatenations above copied the bank, so the FIFO can advance on
+      # its own stream while the losses and their backward run.
+      ev = torch.cuda.Event()
+      ev.record(main)
+      with torch.cuda.stream(streams[4]), torch.no_grad():
+        streams[4].wait_event(ev)
+        for buf, new in ((self.bank_p, protos), (self.bank_sem, p_sem),
+                         (self.bank_mask, cur_mask), (self.bank_live, p_live)):
+          if self.bank_size > 1:
+            buf[:-1] = buf[1:].clone()
+          buf[-1] = new.detach()
 
     # The three losses and the accuracy are independent: each runs on its own stream so
     # that, inside the CUDA graph, they are parallel branches (at batch 1 a single loss only
     # fills ~117 of 148 SMs for a few microseconds).  Autograd replays each backward on the
     # stream of its forward, so the backward passes overlap too.
-    main = torch.cuda.current_stream(dev)
     fork = torch.cuda.Event()
     fork.record(main)
-    streams = self._side_streams
-    for st in streams:
+    for st in streams[:4]:
       st.wait_event(fork)
 
     with torch.cuda.stream(streams[0]):
@@ -154,18 +182,12 @@ class StaticContrastiveHead(nn.Module):
           reduction=_lib.REDUCE_GROUP_MEAN, group_off=img_off, col_off=col_off, num_groups=B,
           n_rows=cap, max_rows_per_group=H * W, name='img_sim')
       img_sim = ops.SegsortLossFn.apply(el, protos_loc, problem) * t.img_sim_loss_weight
-    for st in streams:
+    for st in streams[:4]:
       main.wait_stream(st)
 
     loss = sem_ann + sem_occ + img_sim                                       # train.py:213-219
     loss.backward()
-    with torch.no_grad():
-      if use_bank:                                                           # train.py:276-293
-        for buf, new in ((self.bank_p, protos), (self.bank_sem, p_sem),
-                         (self.bank_mask, cur_mask), (self.bank_live, p_live)):
-          if self.bank_size > 1:
-            buf[:-1] = buf[1:].clone()
-          buf[-1] = new.detach()
+    main.wait_stream(streams[4])
     extra = {}
     if self.collect_stats:     # problem sizes for bench.py's roofline (adds small reductions)
       extra = {'num_labelled_pixels': off[1], 'num_live_prototypes': plive_all.sum(),
