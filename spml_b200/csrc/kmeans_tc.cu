@@ -65,6 +65,7 @@ struct KmeansTcArgs {
   int ksteps;          // 16-wide K steps that hold data
   int stages;          // prototype ring depth (1 or 2)
   int box_rows;        // rows of a TMA box: min(128, K rounded up to 8)
+  int prefetch;        // a second fp32 tile buffer fits: the next tile is fetched with cp.async
   float tau;
 };
 
@@ -248,6 +249,53 @@ __device__ __forceinline__ void finalize_image(const KmeansArgs& p,
     default: { constexpr int kS = 5; CALL; } break; \
   }
 
+// live tile `lt` (image-major order) -> image, first row, row count
+__device__ __forceinline__ void locate_tile(const KmeansArgs& p, int lt, Tile& tile) {
+  int img = 0, base = 0;
+  for (;;) {
+    const int64_t first = p.img_off ? (int64_t)p.img_off[img] : 0;
+    const int64_t last = p.img_off ? (int64_t)p.img_off[img + 1] : p.rows_total;
+    const int tiles_b = (int)((last - first + BM - 1) / BM);
+    if (lt < base + tiles_b) {
+      tile.b = img;
+      tile.row0 = first + (int64_t)(lt - base) * BM;
+      tile.rows = (int)min((int64_t)BM, last - tile.row0);
+      return;
+    }
+    base += tiles_b;
+    ++img;
+  }
+}
+
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Starts the copy of a tile's rows * dim floats into `buf` (kept at the source's 16-byte
+// phase so that the body moves in 16-byte pieces); returns that phase in floats.
+__device__ __forceinline__ int prefetch_tile(const KmeansArgs& p, const Tile& tile, float* buf) {
+  const int tid = threadIdx.x;
+  const float* src = p.x + tile.row0 * p.dim;
+  const int total = tile.rows * p.dim;
+  const int lead = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
+  float* dst = buf + lead;
+  const int head = min(total, (4 - lead) & 3);
+  const int body = (total - head) >> 2;
+  if (tid < head) cp_async_4(dst + tid, src + tid);
+  for (int i = tid; i < body; i += kGemmThreads) cp_async_16(dst + head + 4 * i, src + head + 4 * i);
+  const int done4 = head + 4 * body;
+  if (tid < total - done4) cp_async_4(dst + done4 + tid, src + done4 + tid);
+  cp_async_commit();
+  return lead;
+}
+
 // ------------------------------------------------------------------------- the kernel
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -268,8 +316,18 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const int dim = p.dim;
-  const int total_tiles = p.batch * p.tiles_per_img;
-  const bool resident = (int)gridDim.x >= total_tiles;      // one tile per CTA: load it once
+  // Every CTA takes a CONTIGUOUS range of the live tiles (image-major order): its tiles then
+  // belong to one image (two at a boundary), so it waits for ONE image's prototypes per pass.
+  // With round-robin tiles every CTA visited every image and the finalising CTA of each image
+  // sat on the critical path of all of them, once per image and pass.
+  int live_total = 0;
+  for (int bb = 0; bb < p.batch; ++bb) {
+    const int64_t rows_b = p.img_off ? (int64_t)p.img_off[bb + 1] - p.img_off[bb] : p.rows_total;
+    live_total += (int)((rows_b + BM - 1) / BM);
+  }
+  const int lt0 = (int)((int64_t)live_total * blockIdx.x / gridDim.x);
+  const int lt1 = (int)((int64_t)live_total * (blockIdx.x + 1) / gridDim.x);
+  const bool resident = live_total <= (int)gridDim.x;       // at most one tile per CTA: load it once
   const size_t per_img = (size_t)p.num_clusters * dim;
   const size_t per_iter = (size_t)p.batch * per_img;
   const int dp = a.nkb * 64;
@@ -281,6 +339,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
   uint8_t* b_ring = a_lo + (size_t)a.nkb * kKmBlockBytes;      // [stages][nkb][hi | lo]
   const uint32_t stage_bytes = 2u * a.nkb * kKmBlockBytes;
   float* xf = reinterpret_cast<float*>(b_ring + (size_t)a.stages * stage_bytes);
+  const size_t xf_stride = (size_t)BM * dim + 4;          // a second buffer only with a.prefetch
   const float* xs = xf;   // xs[r * dim + d]: the fp32 tile, at the 16-byte phase of its source
 
   if (tid == 0) {
@@ -306,46 +365,67 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
   const uint32_t ring_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), 16);
 
   uint32_t q = 0;   // column tiles this CTA has pushed through the ring / accumulators so far
+  const bool pf = a.prefetch && !resident && lt0 < lt1;
+  int cur = 0, lead_cur = 0, lead_nxt = 0;
+  if (pf) {
+    Tile first_tile;
+    locate_tile(p, lt0, first_tile);
+    lead_cur = prefetch_tile(p, first_tile, xf);
+  }
 
   for (int it = 0; it <= p.iterations; ++it) {
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int lt = lt0; lt < lt1; ++lt) {
       Tile tile;
-      if (!tile_of(p, t, tile)) continue;
+      locate_tile(p, lt, tile);
       const int b = tile.b;
       const int kb = p.k_per_image ? p.k_per_image[b] : p.num_clusters;
       KMT(0);
       KMT_CTA(0);
 
       if (!resident || it == 0) {
-        // ---- fp32 tile: one contiguous chunk of rows * dim floats, 128-bit copies where the
-        // source allows (the shared copy keeps the source's 16-byte phase)
-        const float* __restrict__ src = p.x + tile.row0 * dim;
-        const int total = tile.rows * dim;
-        const int lead = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
-        float* dst = xf + lead;
-        xs = dst;
-        const int head = min(total, (4 - lead) & 3);
-        const int body = (total - head) >> 2;
-        __syncthreads();   // nobody still reads the previous tile
-        if (tid < head) dst[tid] = src[tid];
-        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src + head);
-        float4* d4 = reinterpret_cast<float4*>(dst + head);
-        for (int i0 = 0; i0 < body; i0 += 4 * kGemmThreads) {   // four 128-bit loads in flight
-          float4 r4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = i0 + j * kGemmThreads + tid;
-            if (i < body) r4[j] = s4[i];
+        float* dst;
+        if (pf) {
+          // ---- the tile was requested one tile ago (cp.async); ask for the next one now
+          cp_async_wait_all();
+          __syncthreads();   // landed for everybody; nobody still reads the previous tile
+          dst = xf + cur * xf_stride + lead_cur;
+          const int nlt = lt + 1 < lt1 ? lt + 1 : (it < p.iterations ? lt0 : -1);
+          if (nlt >= 0) {
+            Tile next;
+            locate_tile(p, nlt, next);
+            lead_nxt = prefetch_tile(p, next, xf + (cur ^ 1) * xf_stride);
           }
+        } else {
+          // ---- fp32 tile: one contiguous chunk of rows * dim floats, 128-bit copies where the
+          // source allows (the shared copy keeps the source's 16-byte phase)
+          const float* __restrict__ src = p.x + tile.row0 * dim;
+          const int total = tile.rows * dim;
+          const int lead = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
+          dst = xf + lead;
+          const int head = min(total, (4 - lead) & 3);
+          const int body = (total - head) >> 2;
+          __syncthreads();   // nobody still reads the previous tile
+          if (tid < head) dst[tid] = src[tid];
+          const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src + head);
+          float4* d4 = reinterpret_cast<float4*>(dst + head);
+          for (int i0 = 0; i0 < body; i0 += 4 * kGemmThreads) {   // four 128-bit loads in flight
+            float4 r4[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = i0 + j * kGemmThreads + tid;
-            if (i < body) d4[i] = r4[j];
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j * kGemmThreads + tid;
+              if (i < body) r4[j] = s4[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j * kGemmThreads + tid;
+              if (i < body) d4[i] = r4[j];
+            }
           }
+          const int done4 = head + 4 * body;
+          if (tid < total - done4) dst[done4 + tid] = src[done4 + tid];
+          __syncthreads();
         }
-        const int done4 = head + 4 * body;
-        if (tid < total - done4) dst[done4 + tid] = src[done4 + tid];
-        __syncthreads();
+        xs = dst;
         // ---- bf16 hi / lo operand tiles in the layout a SWIZZLE_128B TMA box would write
         const int nch = 2 * a.ksteps;   // 8-element chunks that the MMAs read
         for (int idx = tid; idx < nch * BM; idx += kGemmThreads) {
@@ -617,6 +697,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         }
         KMT(10);
       }
+      if (pf) cur ^= 1, lead_cur = lead_nxt;
     }
   }
 
@@ -668,6 +749,11 @@ int kmeans_tc_launch(const KmeansArgs& p, void* split_protos, int sms, cudaStrea
   a.ksteps = (p.dim + 15) / 16;
   a.tau = 1e-4f;
   a.box_rows = std::min(kKmBN, (p.num_clusters + 7) & ~7);
+  const size_t second = ((size_t)BM * p.dim + 4) * sizeof(float);
+  if (smem + second <= 220 * 1024) {
+    a.prefetch = 1;
+    smem += second;
+  }
   const size_t split_rows = (size_t)p.iterations * p.batch * p.num_clusters;
   const size_t split_bytes = align_up(split_rows * a.nkb * 64 * 2, 256);
   char* split = reinterpret_cast<char*>(split_protos);
