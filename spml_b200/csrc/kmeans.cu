@@ -316,17 +316,18 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
 }
 
 // Which E-step runs (both return the same labels, bit for bit).  Measured on B200
-// (profiles/r1c_*): the tcgen05 kernel (one CTA per SM, every phase of a tile in sequence) wins
-// when each CTA keeps its one tile resident, and when the assignment GEMM is big (K >= 512, or
-// K >= 256 with many tiles per SM); with a few tiles per SM and K < 256 the fp32 kernel's
-// 2-4 co-resident CTAs per SM hide the per-tile latencies better.
+// (profiles/r1c_*): the tcgen05 kernel (one CTA per SM) wins when each CTA keeps its one tile
+// resident (batch 1-2 at 128 x 128) and when the assignment GEMM is big (K >= 256: 1.2-2.8x);
+// with several tiles per SM and a small K (the shipped batch 4: 0.48 vs 0.47 ms) the two tie
+// and the fp32 kernel, whose 2-4 co-resident CTAs per SM hide the per-tile latencies, keeps
+// that regime.
 // SPML_B200_KMEANS=fp32|tc overrides (read per call so that tests can compare the two).
 static bool kmeans_use_tc(int dim, int num_clusters, int64_t tiles, int sms) {
   if (!spml::kmeans_tc_supported(dim)) return false;
   const char* e = getenv("SPML_B200_KMEANS");
   if (e && !strcmp(e, "fp32")) return false;
   if (e && !strcmp(e, "tc")) return true;
-  return tiles <= sms || num_clusters >= 512 || (num_clusters >= 256 && tiles >= 8ll * sms);
+  return tiles <= sms || num_clusters >= 256;
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {

@@ -365,6 +365,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
   const uint32_t ring_lo = tc::umma_desc_lo(tc::smem_u32(b_ring), 16);
 
   uint32_t q = 0;   // column tiles this CTA has pushed through the ring / accumulators so far
+  bool tma_ahead = false;   // the next tile's first prototype tile is already in flight
   const bool pf = a.prefetch && !resident && lt0 < lt1;
   int cur = 0, lead_cur = 0, lead_nxt = 0;
   if (pf) {
@@ -460,8 +461,9 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
       } else {
         // ================================================================== E-step
         if (tid == 0) {
+          // (with the prototype tile already requested, this image's flag was seen last tile)
           const unsigned* flag = p.ready + (size_t)(it - 1) * p.batch + b;
-          while (ld_acquire_gpu(flag) == 0) {
+          while (!tma_ahead && ld_acquire_gpu(flag) == 0) {
           }
           s_namb = 0;
         }
@@ -514,11 +516,14 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         };
 
         if (warp == 0 && ntiles > 0) {
-          fence_proxy_async_all();   // prototypes were written through the generic proxy
-          issue_tma(0, q);
+          if (!tma_ahead) {
+            fence_proxy_async_all();   // prototypes were written through the generic proxy
+            issue_tma(0, q);
+          }
           if (a.stages == 2 && ntiles > 1) issue_tma(1, q + 1);
           issue_mma(q);
         }
+        tma_ahead = false;
         KMT(3);
         const int sp = warp & 3;            // TMEM sub-partition of this warp
         const int half = warp >> 2;         // which 32-column chunks of an accumulator
@@ -647,6 +652,20 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         }
         __syncthreads();
         KMT(7);
+        // The next tile of this CTA is usually in the same image and pass: it needs the same
+        // prototypes, and the ring slot is free (this tile's MMAs are complete), so its
+        // first prototype tile is requested now and lands during the M-step.
+        if (!resident && lt + 1 < lt1 && ntiles > 0) {
+          Tile next;
+          locate_tile(p, lt + 1, next);
+          if (next.b == b) {
+            tma_ahead = true;
+            if (warp == 0) {
+              fence_proxy_async_all();   // the exact re-check may have used the ring as scratch
+              issue_tma(0, q);
+            }
+          }
+        }
 #ifdef SPML_KM_TRACE
         if (blockIdx.x == 0 && tid == 0 && it < 16) g_kmt_trace[it * 16 + 15] = namb;
 #endif
