@@ -1152,7 +1152,9 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
   a.ccode = p.ccode;
   a.stats = stats;
   a.grad_loss = grad_loss;
-  a.pm = p.pm;
+  // the weights are published by the pixel-owner kernel only when the prototype-owner kernel of
+  // THIS call reads them (a d(embedding)-only call may run next to a d(prototypes)-only call)
+  a.pm = proto_partial ? p.pm : nullptr;
   a.inv_scale = (float)(1.0 / ((double)d.kappa * 1.4426950408889634));
   a.nkb = p.nkb;
   a.ksteps = p.ksteps;
@@ -1202,6 +1204,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     SPML_LAUNCH_CHECK("segsort_bwd_tc_kernel<emb>");
   }
   if (proto_partial) {
+    a.pm = p.pm;
     if (!demb) {   // nobody has written the per-pixel weights yet
       dim3 pgrid((unsigned)std::max<int64_t>(1, ceil_div(d.max_rows_per_group, 256)),
                  (unsigned)d.num_groups);
