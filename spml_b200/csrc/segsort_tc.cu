@@ -7,14 +7,14 @@
 // TMEM), which keeps ~16 mantissa bits per product: cosines are exact to ~1e-5, inside
 // the 1e-3 parity bar with two orders of margin, at 3/1 of the bf16 MMA cost.
 //
-// Kernel layout (one CTA per 128-row tile, 10 warps):
+// Kernel layout (one CTA per 128-row tile, 18 warps):
 //   warp 0      TMA producer: A tile (all K blocks, hi + lo) once, then the prototype
-//               bank streamed in 128-column tiles through a 2-stage shared-memory ring
-//   warp 1      TMEM allocator and single-thread MMA issuer; accumulators double-buffered
-//               in TMEM (2 x 128 columns) so the epilogue of tile j overlaps the MMAs of j+1
-//   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns, ex2, code compare, running
-//               same / diff / self sums per row; two warps share each TMEM sub-partition
-//               (forward: sixteen warps, one per 32-column quarter)
+//               bank streamed in 128-column tiles through a 4-stage shared-memory ring
+//   warp 1      TMEM allocator and MMA issuer (elect.sync); accumulators double-buffered
+//               in TMEM so the epilogue of tile j overlaps the MMAs of j+1
+//   warps 2-17  epilogue: tcgen05.ld 32 lanes x 32 columns, ex2, code compare, running
+//               same / diff sums per row; four warps share each TMEM sub-partition, one per
+//               32-column quarter of the tile
 #include <math.h>
 
 #include <stdlib.h>
@@ -1130,7 +1130,11 @@ __device__ long long g_tc_trace[64 * 16];
 int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
   const int64_t col_tiles = std::max<int64_t>(1, ceil_div(d.m, kBwdBM));
   const int64_t steps = std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kBwdBN));
-  int64_t chunks = ceil_div(2 * 148, col_tiles * d.num_groups);
+  // with per-group column ranges (img_sim) a group only owns ~1 / num_groups of the column
+  // tiles: the others exit at once, so they must not count as work when the rows are split
+  const int64_t live_tiles = d.col_off ? ceil_div(col_tiles, d.num_groups) * d.num_groups
+                                       : col_tiles * d.num_groups;
+  int64_t chunks = ceil_div(2 * 148, live_tiles);
   // with a column mask the buffer is capacity-sized and most column tiles are dead:
   // keep enough row chunks for the live ones to fill the GPU
   if (d.proto_valid) chunks = std::max<int64_t>(chunks, 16);

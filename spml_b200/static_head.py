@@ -182,12 +182,13 @@ class StaticContrastiveHead(nn.Module):
           reduction=_lib.REDUCE_GROUP_MEAN, group_off=img_off, col_off=col_off, num_groups=B,
           n_rows=cap, max_rows_per_group=H * W, name='img_sim')
       img_sim = ops.SegsortLossFn.apply(el, protos_loc, problem) * t.img_sim_loss_weight
-    for st in streams[:4]:
+    for st in (streams[0], streams[1], streams[3]):
       main.wait_stream(st)
 
     loss = sem_ann + sem_occ + img_sim                                       # train.py:213-219
     loss.backward()
-    main.wait_stream(streams[4])
+    main.wait_stream(streams[2])     # the retrieval accuracy is an output only: it may run on
+    main.wait_stream(streams[4])     # next to the backward pass, like the memory-bank FIFO
     extra = {}
     if self.collect_stats:     # problem sizes for bench.py's roofline (adds small reductions)
       extra = {'num_labelled_pixels': off[1], 'num_live_prototypes': plive_all.sum(),
