@@ -79,7 +79,11 @@ class StaticContrastiveHead(nn.Module):
     self.bank_mask = z(S, M, dtype=torch.int64)
     self.bank_live = z(S, M, dtype=torch.uint8)
     self.out = {}
-    self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
+    # 0, 1, 3: the three losses (high priority: the backward pass waits for them);
+    # 2: top-k, 4: memory-bank FIFO (outputs only)
+    # (measured on one box: 1.490 -> 1.451 ms at batch 4 with the priorities)
+    self._side_streams = [torch.cuda.Stream(device=dev, priority=0 if i in (2, 4) else -1)
+                          for i in range(5)]
 
   # ------------------------------------------------------------------------------ one step
   def _forward(self):
