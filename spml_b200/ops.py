@@ -121,9 +121,11 @@ class NormalizePack(torch.autograd.Function):
     nx = torch.empty(cap, dtype=torch.float32, device=dev)
     nc = torch.empty(cap, dtype=torch.float32, device=dev)
     # rows past the live count are padding: integers read as 0 there (fixed-capacity mode)
-    labels_out = torch.zeros(cap, dtype=torch.int64, device=dev)
-    batch_out = torch.zeros(cap, dtype=torch.int64, device=dev)
-    seed_out = torch.zeros(cap, dtype=torch.int32, device=dev)
+    # (one zero-filled buffer, three views: one fill kernel instead of three)
+    zeros = torch.zeros(cap * 20, dtype=torch.uint8, device=dev)
+    labels_out = zeros[:cap * 8].view(torch.int64)
+    batch_out = zeros[cap * 8:cap * 16].view(torch.int64)
+    seed_out = zeros[cap * 16:].view(torch.int32)
     call('spml_normalize_pack_fwd', ptr(emb), ptr(loc_c), loc_bs, loc_ch, ptr(labels),
          ptr(seeds_c), seed_bs, ptr(dst), B, D, n, int(batch_index_offset), EPS,
          ptr(e), ptr(el), ptr(nx), ptr(nc), ptr(labels_out), ptr(batch_out), ptr(seed_out),

@@ -191,7 +191,7 @@ def segment_core(embeddings, labels, num_clusters, cluster_indices, local_featur
     after_pack(bid)
   _, km = ops.kmeans(el.detach(), img_off, B, n, num_k, iterations, seed, k_per_image)
   # :398-405: rank of (image, cluster, label) among the triples that occur
-  inverse, _, _, count, _ = ops.unique_inverse(lab, hi=bid * num_k + km, bound=0,
+  inverse, _, _, count, _ = ops.unique_inverse(lab, hi=torch.add(km, bid, alpha=num_k), bound=0,
                                                n_dev=img_off[B:], want_keys=False)
   return e, el, lab, inverse, bid, img_off, count, batch_index_offset
 
