@@ -282,6 +282,14 @@ def run_b200(args):
                                  out['accuracy']]), non_blocking=True)
     return out
 
+  def step_e2e_losses(i):
+    # the same with only what train.py reads back every step (losses + accuracy, train.py:213-219);
+    # in training d(embedding) stays on the device and feeds the backbone's backward
+    out = head.step(*args_of(host[i % POOL]))
+    loss_host.copy_(torch.stack([out['sem_ann_loss'], out['sem_occ_loss'], out['img_sim_loss'],
+                                 out['accuracy']]), non_blocking=True)
+    return out
+
   def step_drop_in(i):
     b = resident[i % POOL]
     emb = b['embedding'].detach().requires_grad_(True)
@@ -333,6 +341,7 @@ def run_b200(args):
     kernels_per_step = _lib.launch_count() - before
   ms_res, _, wall_res = timed(step_resident, args.steps, max(args.warmup, 3))
   ms_e2e, _, wall_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+  ms_e2e_l, _, _ = timed(step_e2e_losses, args.steps, max(args.warmup, 3))
   clocks = sampler.stop() if sampler else None
   ms_dyn, _, _ = timed(step_drop_in, max(3, args.steps // 3), 3)
   ms_dyn = ms_dyn / max(3, args.steps // 3)
@@ -346,6 +355,7 @@ def run_b200(args):
     return float(t)
 
   ms_res, ms_e2e = max_over_ranks(ms_res), max_over_ranks(ms_e2e)
+  ms_e2e_l = max_over_ranks(ms_e2e_l)
   images = w.batch * world * args.steps
 
   # ---- per-entry-point profile of a few steps (separate pass; events per C-ABI call)
@@ -437,7 +447,12 @@ def run_b200(args):
         'contrastive_step_ms': ms_res / args.steps,
         'e2e': {'value': images / (ms_e2e * 1e-3), 'unit': 'images/s',
                 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': d2h_bytes},
+                'd2h_bytes_per_step': d2h_bytes,
+                'd2h': 'three losses, accuracy and d(loss)/d(embedding)',
+                # secondary: what a training loop moves (the gradient stays on the device)
+                'losses_only': {'value': images / (ms_e2e_l * 1e-3),
+                                'ms_per_step': ms_e2e_l / args.steps,
+                                'd2h_bytes_per_step': loss_host.numel() * 4}},
         'gpu_launches': launches,
         'gpu_launches_per_step': kernels_per_step,
         'cuda_graph': not args.no_graph,
