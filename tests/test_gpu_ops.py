@@ -173,6 +173,30 @@ def test_topk(units):
   assert torch.equal(maj.cpu(), u['majority'])
 
 
+@pytest.mark.parametrize('m,dim,nq', [(700, 64, 97), (40000, 32, 50), (1500, 130, 40)])
+def test_topk_masks_and_cluster_split(m, dim, nq):
+  """Fixed-capacity banks: dead queries / prototypes are skipped, the bank is split over the
+  8-CTA cluster (m = 40 000 also exceeds the per-CTA live-tile table), and the merged top-5
+  equals a full sort over the live prototypes."""
+  g = torch.Generator().manual_seed(m + dim)
+  p = O.l2_normalize(torch.randn(m, dim, generator=g))
+  q = O.l2_normalize(torch.randn(nq, dim, generator=g))
+  pl, ql = torch.randint(0, 21, (m,), generator=g), torch.randint(0, 21, (nq,), generator=g)
+  pvalid = (torch.rand(m, generator=g) < 0.3)
+  pvalid[m // 3: m // 2] = False                 # whole dead column tiles
+  qvalid = (torch.rand(nq, generator=g) < 0.8)
+  live = torch.nonzero(pvalid).flatten()
+  sim = q[qvalid] @ p[live].t()
+  order = torch.argsort(sim, dim=1, descending=True, stable=True)[:, :5]
+  want = pl[live][order]
+  acc, lab = ops.topk_ranking(cu(q), cu(ql), cu(p), cu(pl), 5, qvalid=cu(qvalid.to(torch.uint8)),
+                              pvalid=cu(pvalid.to(torch.uint8)))
+  got = lab.cpu()[qvalid]
+  assert float((got != want).float().mean()) < 2e-3      # near-ties may swap
+  want_acc = (want == ql[qvalid][:, None]).float().mean()
+  assert abs(float(acc) - float(want_acc)) < 2e-3
+
+
 def test_topk_large_k20():
   g = torch.Generator().manual_seed(11)
   q = O.l2_normalize(torch.randn(333, 64, generator=g))
