@@ -316,18 +316,19 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
 }
 
 // Which E-step runs (both return the same labels, bit for bit).  Measured on B200
-// (profiles/r1c_*): the tcgen05 kernel (one CTA per SM) wins when each CTA keeps its one tile
-// resident (batch 1-2 at 128 x 128) and when the assignment GEMM is big (K >= 256: 1.2-2.8x);
-// with several tiles per SM and a small K (the shipped batch 4: 0.48 vs 0.47 ms) the two tie
-// and the fp32 kernel, whose 2-4 co-resident CTAs per SM hide the per-tile latencies, keeps
-// that regime.
+// (profiles/r1c_*): the tcgen05 kernel wins when each CTA keeps its one tile resident (batch
+// 1 at 128 x 128: 0.175 vs 0.19 ms) and when the assignment GEMM is big (K >= 256: 1.2-2.8x).
+// With several tiles per SM and a small K it ties with the fp32 kernel as long as its second
+// fp32 tile buffer (cp.async prefetch) fits, i.e. up to ~96 channels (the shipped batch 4:
+// 0.455 vs 0.463 ms); without it (D = 128, K = 64: 1.0 vs 0.6 ms) the fp32 kernel's 2-4
+// co-resident CTAs per SM hide the per-tile latencies better and keep that corner.
 // SPML_B200_KMEANS=fp32|tc overrides (read per call so that tests can compare the two).
 static bool kmeans_use_tc(int dim, int num_clusters, int64_t tiles, int sms) {
   if (!spml::kmeans_tc_supported(dim)) return false;
   const char* e = getenv("SPML_B200_KMEANS");
   if (e && !strcmp(e, "fp32")) return false;
   if (e && !strcmp(e, "tc")) return true;
-  return tiles <= sms || num_clusters >= 256;
+  return tiles <= sms || num_clusters >= 256 || dim <= 96;
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {

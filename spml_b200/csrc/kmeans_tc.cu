@@ -366,6 +366,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
 
   uint32_t q = 0;   // column tiles this CTA has pushed through the ring / accumulators so far
   bool tma_ahead = false;   // the next tile's first prototype tile is already in flight
+  int pending = 0;          // tiles of the current image accumulated but not yet counted
   const bool pf = a.prefetch && !resident && lt0 < lt1;
   int cur = 0, lead_cur = 0, lead_nxt = 0;
   if (pf) {
@@ -684,18 +685,31 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap map_ph,
         KM_SLOT_SWITCH(dim, (accumulate_ranked<kS>(p, tile.rows, xs, s_lab, s_order, sums_b)));
         __syncthreads();
         KMT(8);
-        if (tid == 0) {
-          const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
-                                                     : p.rows_total);
-          const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
-          fence_acq_rel_gpu();   // cumulative: the CTA's reductions (ordered by the barrier) first
-          s_last = atomicAdd(p.done + (size_t)it * p.batch + b, 1u) + 1 == tiles_b;
-          fence_acq_rel_gpu();
+        // The CTA's consecutive tiles of one image are counted together: one fence (which has to
+        // wait for the reductions to be performed) and one counter round trip per image and
+        // pass instead of one per tile.
+        ++pending;
+        bool flush_count = lt + 1 >= lt1;
+        if (!flush_count) {
+          Tile next;
+          locate_tile(p, lt + 1, next);
+          flush_count = next.b != b;
         }
-        __syncthreads();
+        if (flush_count) {
+          if (tid == 0) {
+            const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
+                                                       : p.rows_total);
+            const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
+            fence_acq_rel_gpu();   // cumulative: the CTA's reductions (ordered by the barriers) first
+            s_last = atomicAdd(p.done + (size_t)it * p.batch + b, (unsigned)pending) + pending == tiles_b;
+            fence_acq_rel_gpu();
+          }
+          pending = 0;
+          __syncthreads();
+        }
         KMT(9);
         KMT_CTA(2);
-        if (s_last) {
+        if (flush_count && s_last) {
           // ---- the image's last tile is in: fold the replicas, normalise, publish
           KMT_FIN(10);
           KMT_FIN(11);
