@@ -83,7 +83,10 @@ def test_kmeans_matches_oracle(n, dim, k):
 
 @pytest.mark.parametrize('n,dim,k,batch', [(5000, 66, 36, 1), (20000, 66, 36, 3), (3000, 37, 300, 1),
                                            (9000, 128, 1000, 1), (4097, 64, 129, 2),
-                                           (130, 16, 7, 1)])
+                                           (130, 16, 7, 1),
+                                           # several tiles per CTA AND several prototype tiles per
+                                           # pixel tile (two-stage ring, both prefetch paths)
+                                           (30000, 37, 300, 2), (25000, 66, 200, 1)])
 def test_kmeans_tensor_core_equals_fp32(n, dim, k, batch, monkeypatch):
   """The tcgen05 E-step (with its exact re-check of near-ties) and the fp32 CUDA-core
   E-step return identical labels, also on data with no cluster structure (many near-ties)."""
