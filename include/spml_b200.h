@@ -112,8 +112,13 @@ int spml_normalize_pack_bwd(const float* de, const float* del, const float* e,
  *     zero vector) followed by the E-step (argmax of x.P^T, first index on
  *     ties).  Segment sums are accumulated in 64-bit fixed point (2^-32), so
  *     the result does not depend on the order of accumulation.
+ *     The E-step runs as a TMA-fed tcgen05 GEMM (bf16 hi/lo split, near-ties
+ *     re-scored in fp32) or as an fp32 CUDA-core GEMM; both return the same ids
+ *     bit for bit (the choice is made per call from the shape).
  *     labels_out (int32) and labels_out_i64 (nullable) receive the final ids.
- *     workspace: spml_kmeans_workspace_bytes(batch, num_clusters, dim, iterations).
+ *     workspace: spml_kmeans_workspace_bytes(batch, num_clusters, dim, iterations),
+ *     16-byte aligned; the call is one cooperative launch (all its CTAs must be
+ *     able to be resident: it waits for the SMs of concurrently running kernels).
  */
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations);
 int spml_kmeans(const float* x, const int32_t* img_off, int batch,
