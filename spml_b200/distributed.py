@@ -93,3 +93,64 @@ def all_reduce_gradients(parameters, bucket_bytes=64 << 20):
       g.copy_(flat[off:off + g.numel()].view_as(g))
       off += g.numel()
   return len(buckets)
+
+
+# ------------------------------------------------------------------------------ SURVEY.md 8f-1
+#
+# Groundwork for the cross-GPU prototype exchange (the reference contrasts every pixel with
+# the prototypes of ALL GPUs and lets the gradient flow back, spml/models/utils.py:86-127).
+# Segments never span images, so a rank's prototypes are complete on that rank: the
+# exchange is an all-gather of fixed-capacity [M_cap, D] blocks (plus their labels), and
+# its backward a reduce-scatter of d(prototypes).  Not wired into the heads yet (PR1 uses
+# rank-local prototypes, north_star); the collective pair is tested on gloo.
+
+
+class _AllGatherRows(torch.autograd.Function):
+  """y = concat over ranks of x (equal shapes).  Backward: every rank holds a gradient for
+  the whole y; rank r receives the sum over ranks of block r (reduce-scatter)."""
+
+  @staticmethod
+  def forward(ctx, x, group):
+    size = dist.get_world_size(group)
+    x = x.contiguous()
+    out = x.new_empty((size * x.shape[0],) + tuple(x.shape[1:]))
+    try:
+      dist.all_gather_into_tensor(out, x, group=group)
+    except (RuntimeError, NotImplementedError):      # backends without the tensor variant
+      dist.all_gather(list(out.chunk(size, 0)), x, group=group)
+    ctx.group, ctx.rows = group, x.shape[0]
+    return out
+
+  @staticmethod
+  def backward(ctx, grad):
+    grad = grad.contiguous()
+    rank = dist.get_rank(ctx.group)
+    out = grad.new_empty((ctx.rows,) + tuple(grad.shape[1:]))
+    try:
+      dist.reduce_scatter_tensor(out, grad, op=dist.ReduceOp.SUM, group=ctx.group)
+    except (RuntimeError, NotImplementedError):      # gloo: all-reduce, keep the own block
+      total = grad.clone()
+      dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.group)
+      out = total[rank * ctx.rows:(rank + 1) * ctx.rows].clone()
+    return out, None
+
+
+def all_gather_prototypes(prototypes, *labels, group=None):
+  """Gathers the fixed-capacity prototype block of every rank: returns the differentiable
+  [world * M_cap, D] prototypes followed by the gathered label tensors (no gradient).
+  Rank r's block sits at rows [r * M_cap, (r + 1) * M_cap); a pixel's own segment id becomes
+  `r * M_cap + local_id` (`global_segment_ids`).  Single process: the inputs unchanged."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return (prototypes,) + tuple(labels)
+  gathered = [_AllGatherRows.apply(prototypes, group)]
+  for lab in labels:
+    with torch.no_grad():
+      gathered.append(_AllGatherRows.apply(lab.detach(), group))
+  return tuple(gathered)
+
+
+def global_segment_ids(local_ids, m_cap, group=None):
+  """Column of a pixel's own prototype in the gathered bank (negative ids stay negative)."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return local_ids
+  return torch.where(local_ids >= 0, local_ids + dist.get_rank(group) * int(m_cap), local_ids)

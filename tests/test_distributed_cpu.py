@@ -61,3 +61,43 @@ def test_single_process_is_identity():
                        int(os.environ.get('LOCAL_RANK', 0)))
   assert D.max_over_ranks(3.5) == 3.5 and D.sum_over_ranks(2.0) == 2.0
   assert D.all_reduce_gradients([]) == 0
+
+
+def _gather_worker(rank, size, port, out):
+  os.environ.update(RANK=str(rank), WORLD_SIZE=str(size), LOCAL_RANK=str(rank),
+                    MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  D.init('gloo')
+  g = torch.Generator().manual_seed(5)
+  blocks = torch.randn(size, 3, 4, generator=g)            # every rank's prototype block
+  weights = torch.randn(size, size * 3, 4, generator=g)    # every rank's loss weights on the bank
+  x = blocks[rank].clone().requires_grad_(True)
+  labels = torch.arange(3) + 10 * rank
+  bank, bank_labels = D.all_gather_prototypes(x, labels)
+  (bank * weights[rank]).sum().backward()
+  want_bank = blocks.reshape(size * 3, 4)
+  want_grad = weights[:, rank * 3:(rank + 1) * 3].sum(0)   # sum over ranks of the own block
+  ids = D.global_segment_ids(torch.tensor([0, 2, -1]), 3)
+  out[rank] = (torch.allclose(bank.detach(), want_bank), torch.allclose(x.grad, want_grad),
+               bank_labels.tolist(), ids.tolist(), bool(bank_labels.requires_grad))
+  dist.destroy_process_group()
+
+
+def test_prototype_all_gather_and_its_backward():
+  """SURVEY.md 8f-1 groundwork: the gathered bank is the concatenation of the rank blocks and
+  its backward is the reduce-scatter of the bank gradients."""
+  size, port = 2, _free_port()
+  with mp.Manager() as m:
+    out = m.dict()
+    mp.spawn(_gather_worker, args=(size, port, out), nprocs=size, join=True)
+    r0, r1 = out[0], out[1]
+  assert r0[0] and r1[0] and r0[1] and r1[1]
+  assert r0[2] == r1[2] == [0, 1, 2, 10, 11, 12]
+  assert r0[3] == [0, 2, -1] and r1[3] == [3, 5, -1]
+  assert not r0[4] and not r1[4]
+
+
+def test_prototype_all_gather_single_process_is_identity():
+  x, lab = torch.randn(3, 4), torch.arange(3)
+  bank, bank_lab = D.all_gather_prototypes(x, lab)
+  assert bank is x and bank_lab is lab
+  assert D.global_segment_ids(lab, 3) is lab
