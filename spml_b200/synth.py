@@ -49,6 +49,12 @@ class Workload:
   sem_occ_loss_weight: float = 0.5
   img_sim_loss_weight: float = 0.1
   loc_channels: int = 2        # location (y, x); DensePose adds RGB -> 5
+  # which head: 'segsort' (predictions/segsort.py), 'softmax' (segsort_softmax.py, the class
+  # train.py instantiates) or 'densepose' (resnet_pspnet_densepose.py generate_clusters +
+  # segsort_softmax_densepose.py)
+  variant: str = 'segsort'
+  sem_occ_loss_types: str = 'segsort'
+  label_upsample: int = 1      # > 1: also emit the full-resolution label map (classifier CE)
 
 
 WORKLOADS = {
@@ -59,11 +65,23 @@ WORKLOADS = {
     # BASELINE.json configs[2]: image tags (CAM), 2 img/GPU, 8x8 seeds.
     'voc_tag_b2': Workload(name='voc_tag_b2', batch=2, num_clusters=(8, 8),
                            rho=0.6, sem_occ_concentration=8.0),
-    # BASELINE.json configs[3]: DensePose-like, 769 crop -> 194x194, D=32.
+    # BASELINE.json configs[3]: DensePose points, 769 crop -> 194x194, D=32, 128 seeds,
+    # location + RGB features, the DensePose head (1-NN tag propagation over
+    # prototype_with_loc, img_sim on the plain embeddings), no memory bank, sem_occ off
+    # (bashscripts/densepose/train_spml_point.sh:14-44).
     'densepose_b1': Workload(name='densepose_b1', batch=1, height=194,
                              width=194, dim=32, num_clusters=(8, 16),
                              num_classes=15, rho=0.02, memory_bank_size=0,
-                             sem_occ_concentration=8.0),
+                             sem_occ_concentration=8.0, loc_channels=5,
+                             variant='densepose', sem_occ_loss_types='none'),
+    # the same shapes through the VOC head (round-1 workload, kept for comparison)
+    'densepose_shape_voc_head_b1': Workload(
+        name='densepose_shape_voc_head_b1', batch=1, height=194, width=194, dim=32,
+        num_clusters=(8, 16), num_classes=15, rho=0.02, memory_bank_size=0,
+        sem_occ_concentration=8.0, loc_channels=5),
+    # the softmax head train.py instantiates (segsort_softmax.py) at the VOC shapes
+    'voc_scribble_softmax_b1': Workload(name='voc_scribble_softmax_b1', variant='softmax',
+                                        label_upsample=4),
     # small cases used by the parity tests / golden vectors.
     'tiny': Workload(name='tiny', batch=2, height=24, width=20, dim=16,
                      num_clusters=(3, 3), num_regions=9, iterations=10,
@@ -71,6 +89,19 @@ WORKLOADS = {
     'small': Workload(name='small', batch=2, height=40, width=32, dim=24,
                       num_clusters=(4, 4), num_regions=16, rho=0.2,
                       memory_bank_size=2),
+    'tiny_softmax': Workload(name='tiny_softmax', batch=2, height=24, width=20, dim=16,
+                             num_clusters=(3, 3), num_regions=9, rho=0.3, memory_bank_size=1,
+                             variant='softmax', label_upsample=2),
+    # DensePose head with every branch on: sem_occ enabled and a memory bank
+    'tiny_densepose': Workload(name='tiny_densepose', batch=2, height=24, width=20, dim=16,
+                               num_clusters=(3, 3), num_regions=9, rho=0.3, memory_bank_size=1,
+                               num_classes=15, loc_channels=5, variant='densepose',
+                               sem_occ_concentration=8.0),
+    # ... and as shipped (sem_occ off, no bank)
+    'tiny_densepose_shipped': Workload(
+        name='tiny_densepose_shipped', batch=2, height=24, width=20, dim=16,
+        num_clusters=(3, 3), num_regions=9, rho=0.3, memory_bank_size=0, num_classes=15,
+        loc_channels=5, variant='densepose', sem_occ_loss_types='none'),
 }
 
 
@@ -84,7 +115,7 @@ def make_config(w: Workload) -> SimpleNamespace:
                               kmeans_iterations=w.iterations,
                               kmeans_num_clusters=list(w.num_clusters)),
       train=SimpleNamespace(
-          sem_ann_loss_types='segsort', sem_occ_loss_types='segsort',
+          sem_ann_loss_types='segsort', sem_occ_loss_types=w.sem_occ_loss_types,
           img_sim_loss_types='segsort', feat_aff_loss_types='none',
           sem_ann_concentration=w.sem_ann_concentration,
           sem_occ_concentration=w.sem_occ_concentration,
@@ -114,6 +145,7 @@ def make_batch(w: Workload, seed: int = 235, step: int = 0):
   instance_label  [B, H, W] int64   (over-segmentation id < 256)
   semantic_tag    [B, 256] int64    (1 where the class occurs in the image)
   local_feature   [B, H, W, loc_channels] float32
+  semantic_label_full [B, H*u, W*u] int64, only when w.label_upsample = u > 1
   """
   g = torch.Generator().manual_seed(seed * 1000003 + step)
   B, H, W, D = w.batch, w.height, w.width, w.dim
@@ -157,8 +189,14 @@ def make_batch(w: Workload, seed: int = 235, step: int = 0):
     local = torch.cat([loc[None].expand(B, H, W, 2), rgb], dim=-1).contiguous()
   else:
     local = loc[None].expand(B, H, W, 2).contiguous()
-  return {'embedding': emb, 'semantic_label': sem, 'instance_label': inst,
-          'semantic_tag': tags, 'local_feature': local}
+  out = {'embedding': emb, 'semantic_label': sem, 'instance_label': inst,
+         'semantic_tag': tags, 'local_feature': local}
+  if w.label_upsample > 1:
+    # targets['semantic_label'] of the softmax heads is the full-resolution map; the one the
+    # clustering sees is its nearest-neighbour resize (resnet_deeplab.py:163-167)
+    u = w.label_upsample
+    out['semantic_label_full'] = sem.repeat_interleave(u, 1).repeat_interleave(u, 2)
+  return out
 
 
 def sweep_problem(n_pix: int, dim: int, n_seg: int, seed: int = 235):

@@ -51,24 +51,42 @@ def load_reference():
   import spml.utils.segsort.eval as E
   import spml.utils.general.common as G
   import spml.models.predictions.segsort as P
+  import spml.models.predictions.segsort_softmax as PS
+  import spml.models.predictions.segsort_softmax_densepose as PD
+  import spml.models.embeddings.resnet_deeplab as ED
+  import spml.models.embeddings.resnet_pspnet_densepose as EP
   return types.SimpleNamespace(common=mod, loss=L, eval=E, general=G, model_utils=MU,
-                               segsort=P)
+                               segsort=P, segsort_softmax=PS, segsort_softmax_densepose=PD,
+                               deeplab=ED.ResnetDeeplab, pspnet_densepose=EP.ResnetPspnet)
 
 
-def reference_step(ref, cfg, batch, bank):
-  """Appendix A of SURVEY.md: A9 -> B1 -> B2 -> Segsort.forward -> backward."""
-  C = ref.common
+def reference_model(ref, cfg, variant, classifier_state=None):
+  """The reference's prediction model for a workload variant; the softmax variants get
+  the seeded classifier weights and run in eval mode (dropout p = 0.75 draws from the
+  global RNG in train mode, which no other device reproduces)."""
+  if variant == 'segsort':
+    return ref.segsort.segsort(cfg)
+  mod = ref.segsort_softmax_densepose if variant == 'densepose' else ref.segsort_softmax
+  model = mod.segsort(cfg)
+  model.semantic_classifier.load_state_dict(classifier_state)
+  return model.eval()
+
+
+def reference_step(ref, cfg, batch, bank, variant='segsort', classifier_state=None):
+  """Appendix A of SURVEY.md: A9 (the reference's own generate_clusters method, called on
+  a stand-in `self` that carries the four attributes it reads) -> B1 -> B2 ->
+  prediction model forward -> backward."""
   emb = batch['embedding'].clone().requires_grad_(True)
   sem, inst = batch['semantic_label'], batch['instance_label']
-  div = cfg.network.label_divisor
-  labels = sem * div + inst                                   # resnet_deeplab.py:112-117
-  ign = labels.max() + 1
-  labels = labels.masked_fill(sem == cfg.dataset.semantic_ignore_index, ign)
-  ce, cel, cl, ci, cb = C.segment_by_kmeans(
-      emb, labels, cfg.network.kmeans_num_clusters,
-      local_features=batch['local_feature'], ignore_index=ign,
-      iterations=cfg.network.kmeans_iterations)
-  csl, cil = cl // div, cl % div
+  me = types.SimpleNamespace(label_divisor=cfg.network.label_divisor,
+                             semantic_ignore_index=cfg.dataset.semantic_ignore_index,
+                             kmeans_num_clusters=cfg.network.kmeans_num_clusters,
+                             kmeans_iterations=cfg.network.kmeans_iterations)
+  net = ref.pspnet_densepose if variant == 'densepose' else ref.deeplab
+  cl = net.generate_clusters(me, emb, sem, inst, batch['local_feature'])
+  ce, cel = cl['cluster_embedding'], cl['cluster_embedding_with_loc']
+  csl, cil = cl['cluster_semantic_label'], cl['cluster_instance_label']
+  ci, cb = cl['cluster_index'], cl['cluster_batch_index']
   p, pl, psl, pil, pbi, ci2 = ref.model_utils.gather_clustering_and_update_prototypes(
       [ce], [cel], [ci], [cb], [csl], [cil], 'cpu')
   datas = dict(cluster_index=ci2[0], cluster_embedding=ce, cluster_embedding_with_loc=cel,
@@ -76,21 +94,32 @@ def reference_step(ref, cfg, batch, bank):
                cluster_batch_index=cb)
   tags = batch['semantic_tag']
   targets = dict(prototype=p[0], prototype_with_loc=pl[0], prototype_semantic_label=psl[0],
-                 prototype_instance_label=pil[0], prototype_batch_index=pbi[0],
-                 semantic_tag=tags,
-                 prototype_semantic_tag=tags.index_select(0, pbi[0]))   # train.py:199-202
+                 prototype_instance_label=pil[0], prototype_batch_index=pbi[0])
+  if variant != 'densepose':      # train_densepose.py:189-199 has the tag gather commented out
+    targets.update(semantic_tag=tags,
+                   prototype_semantic_tag=tags.index_select(0, pbi[0]))   # train.py:199-202
   targets.update({k: list(v) for k, v in bank.items()})
-  model = ref.segsort.segsort(cfg)
+  model = reference_model(ref, cfg, variant, classifier_state)
+  if variant != 'segsort':
+    datas['embedding'] = emb
+    targets['semantic_label'] = batch.get('semantic_label_full', sem).clone()
   out = model(datas, targets)
-  total = out['sem_ann_loss'] + out['sem_occ_loss'] + out['img_sim_loss']
+  losses = [out[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss')
+            if out[k] is not None]
+  total = sum(losses)                                                    # train.py:213-219
   total.backward()
+  datas.pop('embedding', None)
+  targets.pop('semantic_label', None)
   res = {k: v.detach().clone() for k, v in datas.items()}
   res['cluster_index_before_gather'] = ci.detach().clone()
   res.update({k: v.detach().clone() for k, v in targets.items() if torch.is_tensor(v)})
-  res.update({k: out[k].detach().clone() for k in
-              ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss', 'accuracy')})
+  for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss', 'accuracy'):
+    res[k] = out[k].detach().clone() if out[k] is not None else torch.zeros(())
   res['loss'] = total.detach().clone()
   res['grad_embedding'] = emb.grad.detach().clone()
+  if variant != 'segsort':
+    res['grad_classifier'] = {k: v.grad.detach().clone()
+                              for k, v in model.semantic_classifier.named_parameters()}
   return res, targets
 
 
@@ -113,10 +142,14 @@ def golden_steps(ref, name, steps, seed=235):
   cfg = synth.make_config(w)
   bank = {}
   files = []
+  state = None
+  if w.variant != 'segsort':
+    from oracle import spml_oracle as O      # only for the seeded classifier WEIGHTS (inputs)
+    state = O.make_classifier(cfg).state_dict()
   for s in range(steps):
     batch = synth.make_batch(w, seed=seed, step=s)
     bank_in = {k: [t.clone() for t in v] for k, v in bank.items()}
-    res, targets = reference_step(ref, cfg, batch, bank)
+    res, targets = reference_step(ref, cfg, batch, bank, w.variant, state)
     fn = os.path.join(HERE, '%s_step%d.pt' % (name, s))
     torch.save({'inputs': batch, 'bank': bank_in, 'outputs': res,
                 'meta': {'workload': name, 'seed': seed, 'step': s,
@@ -217,6 +250,92 @@ def golden_units(ref):
   return [fn]
 
 
+def golden_units2(ref):
+  """Round-2 unit cases (their own file and RNG stream, so units.pt stays byte-stable):
+  NN tag propagation, retrieval predictions, segment_mean, one_hot, list gathers."""
+  g = torch.Generator().manual_seed(236)
+  C, E, G, MU = ref.common, ref.eval, ref.general, ref.model_utils
+  u = {}
+  # f3: same-image top-k neighbours with a class label; image 2 has no labelled prototype
+  # (every neighbour is masked -> no tag), threshold cuts the far ones.
+  M, D, NC = 40, 7, 6
+  base = G.normalize_embedding(torch.randn(8, D, generator=g))
+  protos = G.normalize_embedding(base[torch.randint(0, 8, (M,), generator=g)]
+                                 + 0.15 * torch.randn(M, D, generator=g))
+  pbid = torch.sort(torch.randint(0, 3, (M,), generator=g))[0]
+  psem = torch.randint(0, NC + 2, (M,), generator=g)
+  psem[pbid == 2] = NC
+  for k, thr in ((1, 0.95), (3, 0.9)):
+    u['nn_tags_k%d' % k] = {
+        'p': protos, 'psem': psem, 'pbid': pbid, 'num_classes': NC, 'top_k': k,
+        'threshold': thr,
+        'tags': MU.gather_multiset_labels_per_batch_by_nearest_neighbor(
+            protos, protos, psem, pbid, pbid, num_classes=NC, top_k=k, threshold=thr)}
+  q = G.normalize_embedding(protos[:25] + 0.05 * torch.randn(25, D, generator=g))
+  qbid = pbid[:25].clone()
+  u['nn_tags_queries'] = {
+      'q': q, 'qbid': qbid, 'p': protos, 'psem': psem, 'pbid': pbid, 'num_classes': NC,
+      'top_k': 2, 'threshold': 0.8,
+      'tags': MU.gather_multiset_labels_per_batch_by_nearest_neighbor(
+          q, protos, psem, qbid, pbid, num_classes=NC, top_k=2, threshold=0.8)}
+  # f2: Segsort.predictions (top-20 retrieval + majority vote) with non-dense cluster ids
+  N, D2, NB = 300, 12, 90
+  cid = torch.randint(0, 23, (N,), generator=g) * 3 + 5
+  centres = G.normalize_embedding(torch.randn(75, D2, generator=g))
+  emb = G.normalize_embedding(centres[cid] + 0.3 * torch.randn(N, D2, generator=g))
+  bank = G.normalize_embedding(centres[torch.randint(0, 75, (NB,), generator=g)]
+                               + 0.3 * torch.randn(NB, D2, generator=g))
+  bank_lab = torch.randint(0, 5, (NB,), generator=g)
+  cfg = synth.make_config(synth.WORKLOADS['tiny'])
+  pred, topk = ref.segsort.segsort(cfg).predictions(
+      {'cluster_embedding': emb, 'cluster_index': cid},
+      {'semantic_memory_prototype': bank, 'semantic_memory_prototype_label': bank_lab})
+  u['predictions'] = {'emb': emb, 'cid': cid, 'bank': bank, 'bank_label': bank_lab,
+                      'pred': pred, 'topk': topk}
+  # general/common.py: segment_mean with an empty segment, one_hot
+  x = torch.randn(50, 6, generator=g)
+  idx = torch.randint(0, 9, (50,), generator=g)
+  idx[idx == 4] = 3
+  u['segment_mean'] = {'x': x, 'index': idx, 'mean': G.segment_mean(x, idx)}
+  lab = torch.randint(0, 5, (4, 7), generator=g)
+  u['one_hot'] = {'labels': lab, 'auto': G.one_hot(lab), 'wide': G.one_hot(lab, 8)}
+  # B2: gather_and_update_datas over a two-entry list
+  a, b = torch.randint(0, 2, (2, 256), generator=g), torch.randint(0, 2, (3, 256), generator=g)
+  got = MU.gather_and_update_datas([a, b], 'cpu')
+  u['gather_datas'] = {'in': [a, b], 'out': [t.clone() for t in got]}
+  # B1 over a two-entry list (the reference's multi-GPU semantics: global batch indices)
+  w = synth.WORKLOADS['tiny']
+  cfgw = synth.make_config(w)
+  me = types.SimpleNamespace(label_divisor=cfgw.network.label_divisor,
+                             semantic_ignore_index=cfgw.dataset.semantic_ignore_index,
+                             kmeans_num_clusters=cfgw.network.kmeans_num_clusters,
+                             kmeans_iterations=cfgw.network.kmeans_iterations)
+  lists = {k: [] for k in ('cluster_embedding', 'cluster_embedding_with_loc', 'cluster_index',
+                           'cluster_batch_index', 'cluster_semantic_label',
+                           'cluster_instance_label')}
+  batches = []
+  for dev in range(2):
+    batch = synth.make_batch(w, seed=240 + dev)
+    batches.append(batch)
+    cl = ref.deeplab.generate_clusters(me, batch['embedding'], batch['semantic_label'],
+                                       batch['instance_label'], batch['local_feature'])
+    cl['cluster_batch_index'] = cl['cluster_batch_index'] + dev * w.batch   # common.py:376-377
+    for k in lists:
+      lists[k].append(cl[k].detach())
+  out = MU.gather_clustering_and_update_prototypes(
+      lists['cluster_embedding'], lists['cluster_embedding_with_loc'], lists['cluster_index'],
+      lists['cluster_batch_index'], lists['cluster_semantic_label'],
+      lists['cluster_instance_label'], 'cpu')
+  u['gather_two_devices'] = {
+      'inputs': batches, 'lists': lists,
+      'out': {k: [t.detach().clone() for t in v] for k, v in zip(
+          ('prototype', 'prototype_with_loc', 'prototype_semantic_label',
+           'prototype_instance_label', 'prototype_batch_index', 'cluster_index'), out)}}
+  fn = os.path.join(HERE, 'units2.pt')
+  torch.save(u, fn)
+  return [fn]
+
+
 def main():
   torch.manual_seed(235)
   torch.set_num_threads(1)      # fixed summation order for the fixtures
@@ -224,6 +343,10 @@ def main():
   files = golden_units(ref)
   files += golden_steps(ref, 'tiny', 3)
   files += golden_steps(ref, 'small', 3)
+  files += golden_units2(ref)
+  files += golden_steps(ref, 'tiny_softmax', 3)
+  files += golden_steps(ref, 'tiny_densepose', 2)
+  files += golden_steps(ref, 'tiny_densepose_shipped', 1)
   for f in files:
     print('%8d  %s' % (os.path.getsize(f), os.path.relpath(f, ROOT)))
 

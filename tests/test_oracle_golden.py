@@ -97,14 +97,68 @@ def test_segment_by_kmeans_edges(units):
     same(a, u[k])
 
 
-@pytest.mark.parametrize('name', ['tiny', 'small'])
-def test_full_step_matches_reference(name):
-  """Three consecutive steps (memory bank filling up) of the whole path."""
+@pytest.fixture(scope='module')
+def units2():
+  return load_golden('units2.pt')
+
+
+def test_nn_multiset_labels(units2):
+  """models/utils.py:157-223 (DensePose tag propagation)."""
+  for key in ('nn_tags_k1', 'nn_tags_k3'):
+    u = units2[key]
+    same(O.nn_multiset_labels(u['p'], u['p'], u['psem'], u['pbid'], u['pbid'], u['num_classes'],
+                              u['top_k'], u['threshold']), u['tags'])
+  u = units2['nn_tags_k1']
+  assert int(u['tags'][u['pbid'] == 2].sum()) == 0       # image without a labelled prototype
+  assert int(u['tags'].sum()) > 0
+  u = units2['nn_tags_queries']
+  same(O.nn_multiset_labels(u['q'], u['p'], u['psem'], u['qbid'], u['pbid'], u['num_classes'],
+                            u['top_k'], u['threshold']), u['tags'])
+
+
+def test_predictions(units2):
+  """segsort.py:68-125 (retrieval inference)."""
+  u = units2['predictions']
+  pred, topk = O.segsort_predictions(
+      {'cluster_embedding': u['emb'], 'cluster_index': u['cid']},
+      {'semantic_memory_prototype': u['bank'], 'semantic_memory_prototype_label': u['bank_label']})
+  same(pred, u['pred'])
+  same(topk, u['topk'])
+
+
+def test_segment_mean_one_hot_gather(units2):
+  u = units2['segment_mean']
+  same(O.segment_mean(u['x'], u['index']), u['mean'])
+  assert u['mean'][4].abs().max() == 0                   # empty segment: 0 / 1
+  u = units2['one_hot']
+  same(O.one_hot(u['labels']), u['auto'])
+  same(O.one_hot(u['labels'], 8), u['wide'])
+  u = units2['gather_datas']
+  for t in u['out']:
+    same(t, torch.cat(u['in'], 0))
+  u = units2['gather_two_devices']
+  L = u['lists']
+  out = O.gather_and_update_prototypes(
+      L['cluster_embedding'], L['cluster_embedding_with_loc'], L['cluster_index'],
+      L['cluster_batch_index'], L['cluster_semantic_label'], L['cluster_instance_label'])
+  for got, key in zip(out, ('prototype', 'prototype_with_loc', 'prototype_semantic_label',
+                            'prototype_instance_label', 'prototype_batch_index',
+                            'cluster_index')):
+    for a, b in zip(got, u['out'][key]):
+      same(a, b)
+
+
+@pytest.mark.parametrize('name,steps', [('tiny', 3), ('small', 3), ('tiny_softmax', 3),
+                                        ('tiny_densepose', 2), ('tiny_densepose_shipped', 1)])
+def test_full_step_matches_reference(name, steps):
+  """Consecutive steps (memory bank filling up) of the whole path, for the three heads:
+  segsort.py, segsort_softmax.py (eval mode) and the DensePose variant."""
   w = synth.WORKLOADS[name]
   cfg = synth.make_config(w)
   torch.set_num_threads(1)
   bank = {}
-  for step in range(3):
+  classifier = O.make_classifier(cfg).eval() if w.variant != 'segsort' else None
+  for step in range(steps):
     g = load_golden('%s_step%d.pt' % (name, step))
     batch = synth.make_batch(w, seed=g['meta']['seed'], step=step)
     for k, v in g['inputs'].items():      # the generator is reproducible
@@ -113,9 +167,13 @@ def test_full_step_matches_reference(name):
       assert len(v) == len(bank[k])
       for a, b in zip(bank[k], v):
         same(a, b)
-    out = O.contrastive_step(cfg, batch, bank)
+    out = O.contrastive_step(cfg, batch, bank, variant=w.variant, classifier=classifier)
     for k, v in g['outputs'].items():
       if k == 'cluster_index_before_gather':
+        continue
+      if k == 'grad_classifier':
+        for name_, grad in v.items():
+          same(out[k][name_], grad)
         continue
       same(out[k], v)
     targets = {k: out[k] for k in out if k.startswith('prototype')}
