@@ -39,6 +39,7 @@ extern "C" {
 
 #define SPML_MAX_DIM 136   /* largest embedding dim (incl. location channels) */
 #define SPML_MAX_TOPK 32
+#define SPML_MAX_BANK 8    /* memory-bank entries one spml_head_* call can take */
 
 /* thread-local text of the last error on this thread ("" if none). */
 const char* spml_last_error(void);
@@ -47,6 +48,9 @@ int spml_abi_version(void);
 /* diagnostics: number of kernels this library has launched (all threads) since it
  * was loaded (memsets are not counted). */
 uint64_t spml_debug_launch_count(void);
+/* sizeof the argument structs below (0: spml_segsort_desc, 1: spml_cluster_args, 2:
+ * spml_head_args), so that a binding can check its own struct layout at load time. */
+size_t spml_sizeof_struct(int which);
 
 /* ---------------------------------------------------------------------------
  * A1. spml/utils/general/common.py:101-120 normalize_embedding
@@ -67,7 +71,9 @@ int spml_normalize_rows_bwd(const float* dy, const float* y, const float* norms,
  *
  * spml_valid_scan: dst[b*n+p] = output row of pixel p of image b, or -1 when
  *     it is ignored; img_off[b] = first output row of image b, img_off[batch] =
- *     number of kept pixels.  has_ignore == 0 keeps everything.  src (nullable,
+ *     number of kept pixels.  has_ignore == 0 keeps everything, 1 drops the pixels whose
+ *     label == ignore_index, 2 keeps only the pixels whose label < ignore_index (the
+ *     labelled-pixel filter of segsort.py:184-185).  src (nullable,
  *     capacity batch*n) is the inverse map: src[row] = b*n+p.  ignore_index_dev
  *     (nullable, device) overrides ignore_index when the value only exists on
  *     the device (resnet_deeplab.py:113 computes it as labels.max() + 1).
@@ -271,6 +277,165 @@ int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int
                       const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
                       const uint8_t* pvalid, int k, int64_t* topk_labels,
                       int64_t* topk_index, int32_t* hit_count, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * f3. spml/models/utils.py:157-223 gather_multiset_labels_per_batch_by_nearest_neighbor:
+ *     for every query row the top_k most similar prototypes (q.p) among those with
+ *     pgroup == qgroup[row] (nullable: no group restriction) and plab < num_classes;
+ *     tags[row, c] = 1 iff one of them has plab == c and similarity >= threshold
+ *     ([nq, num_classes] int64, nullable); masks[row] = the same as a bit mask (nullable,
+ *     num_classes <= 64).  workspace: spml_nn_multiset_labels_workspace_bytes(nq, top_k).
+ */
+size_t spml_nn_multiset_labels_workspace_bytes(int64_t nq, int top_k);
+int spml_nn_multiset_labels(const float* q, int64_t nq, const float* p, int64_t m, int dim,
+                            const int64_t* plab, const int64_t* qgroup, const int64_t* pgroup,
+                            int num_classes, int top_k, float threshold, int64_t* tags,
+                            int64_t* masks, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* ===========================================================================
+ * Stage-group entry points: one call per stage of the reference's training step
+ * (pyscripts/train/train.py:167-219), each enqueueing every kernel of its stage.  Kernels
+ * of a stage that do not depend on each other run on side streams owned by the library
+ * (a lazily created pool per host thread and device; they fork from and join back into
+ * `stream`, so for the caller all work is ordered on `stream`).
+ *
+ * A8 whole. spml/utils/segsort/common.py:270-408 segment_by_kmeans (+ the label packing
+ *     of resnet_deeplab.py:112-117 on the caller's side): valid-pixel scan, NCHW -> packed
+ *     normalised rows (+ location features), spherical k-means per image, final segment
+ *     ids = rank of (image, cluster, label).  Buffers have the capacity batch * n rows;
+ *     img_off[batch] (rows kept) and num_segments[0] stay on the device.  `seeds` must be
+ *     dense ids in [0, num_clusters) (k_per_image: per-image cluster counts, nullable).
+ *     workspace: spml_segment_by_kmeans_workspace_bytes(batch, n, dim + loc_ch,
+ *     num_clusters, iterations), 256-byte aligned.
+ */
+typedef struct spml_cluster_args {
+  const float* emb;             /* [batch, dim, n] */
+  const float* loc;             /* [*, n, loc_ch], nullable when loc_ch == 0 */
+  int64_t loc_batch_stride;     /* elements; 0 = one map for every image */
+  const int64_t* labels;        /* [batch, n]; or NULL with sem / inst below */
+  /* resnet_deeplab.py:112-117 inside the call: label = sem * label_divisor + inst, pixels
+     with sem == semantic_ignore are dropped (labels == NULL; has_ignore etc. unused) */
+  const int64_t* sem;           /* [batch, n] or NULL */
+  const int64_t* inst;          /* [batch, n] or NULL */
+  int64_t label_divisor;
+  int64_t semantic_ignore;
+  const int64_t* ignore_index_dev; /* nullable: overrides ignore_index */
+  int64_t ignore_index;
+  const int64_t* seeds;         /* [*, n] */
+  int64_t seed_batch_stride;    /* elements; 0 = one map for every image */
+  const int32_t* k_per_image;   /* [batch] or NULL */
+  int64_t batch_index_offset;
+  int32_t batch, dim, n, loc_ch;
+  int32_t num_clusters, iterations, has_ignore, reserved;
+  float eps;
+  float reserved_f;
+  /* outputs (capacity batch * n rows) */
+  float* e;                     /* [cap, dim] */
+  float* el;                    /* [cap, dim + loc_ch] */
+  float* nx;                    /* [cap] */
+  float* nc;                    /* [cap] */
+  int64_t* labels_out;          /* [cap] */
+  int64_t* batch_out;           /* [cap] */
+  int64_t* segment_ids;         /* [cap] */
+  int64_t* sem_out;             /* [cap] labels_out / label_divisor (nullable) */
+  int64_t* inst_out;            /* [cap] labels_out % label_divisor (nullable) */
+  int32_t* dst;                 /* [batch * n] pixel -> row or -1 */
+  int32_t* img_off;             /* [batch + 1] */
+  int32_t* kmeans_labels;       /* [cap] */
+  int32_t* seed_out;            /* [cap] */
+  int32_t* num_segments;        /* [1] */
+} spml_cluster_args;
+
+size_t spml_segment_by_kmeans_workspace_bytes(int batch, int n, int dim_total, int num_clusters,
+                                              int iterations);
+int spml_segment_by_kmeans(const spml_cluster_args* args, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* B1 for ids fresh from A8. spml/models/utils.py:95-116: the ids are already the dense
+ *     ranks of (image, cluster, label), so both re-numberings are the identity; what is
+ *     left are the per-segment labels (p_sem / p_inst / p_batch [m], nullable; every pixel
+ *     of a segment must carry the same values: a violation sets bit 0 of status[0], an id
+ *     outside [0, m) bit 1; the word is never cleared here) and the two prototype sets
+ *     (el / protos_loc nullable).  bwd: de / del from dprotos / dprotos_loc (either NULL).
+ *     workspace: spml_gather_prototypes_workspace_bytes(m, dim, dim_loc).
+ */
+size_t spml_gather_prototypes_workspace_bytes(int64_t m, int dim, int dim_loc);
+int spml_gather_prototypes_fwd(const float* e, const float* el, int64_t rows, int dim, int dim_loc,
+                               const int64_t* seg, const int64_t* batch, const int64_t* sem,
+                               const int64_t* inst, int64_t m, float eps, float* protos,
+                               float* protos_loc, float* norms, float* norms_loc, int64_t* p_sem,
+                               int64_t* p_inst, int64_t* p_batch, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int spml_gather_prototypes_bwd(const float* dprotos, const float* dprotos_loc, const float* protos,
+                               const float* protos_loc, const float* norms, const float* norms_loc,
+                               const int64_t* seg, int64_t rows, int dim, int dim_loc, int64_t m,
+                               float eps, float* de, float* del, void* stream);
+
+/* C4. losses() of spml/models/predictions/segsort.py:127-243, segsort_softmax.py:133-242
+ *     and segsort_softmax_densepose.py:134-252 (everything but the conv classifier):
+ *     memory-bank concatenation, tag masks, the labelled-pixel / labelled-prototype filter
+ *     of sem_ann, per-image prototypes and row groups of img_sim, the three SegSort
+ *     losses and the top-5 retrieval accuracy.
+ *       enable: bit 0 sem_ann, 1 sem_occ, 2 img_sim, 3 accuracy.
+ *       tags:   nn_tags == 0: image-tag columns [tag_col0, tag_col1) of img_tags
+ *               [tag_rows, img_tags_ld] (row = the pixel's batch index) and of ptags /
+ *               bank_tags (one row per prototype);  nn_tags == 1 (DensePose): 1-NN
+ *               propagation over protos_loc / bank_protos_loc within an image (pbid /
+ *               bank_pbid), threshold nn_threshold, no tag -> every tag.
+ *       img_sim_on_plain: img_sim runs on e (DensePose) instead of el.
+ *       max_groups: upper bound on the images the rows span (bid[last] - bid[0] + 1); a
+ *               violation sets bit 2 of status[0] (nullable).
+ *       wide_tags: more than 32 tag columns (keeps sem_occ off the tcgen05 kernels, whose
+ *               epilogue compares 32-bit codes).
+ *     fwd writes out[0..3] = {w_ann sem_ann, w_occ sem_occ, w_sim img_sim, accuracy} and
+ *     leaves what the backward needs in `state` (spml_head_workspace_bytes(args),
+ *     256-byte aligned, untouched between the two calls).  bwd takes the three incoming
+ *     gradients as device scalars (NULL = zero) and writes de [n, dim], del [n, dim_loc]
+ *     (nullable when unused) and dprotos [m, dim] (nullable; memory-bank prototypes are
+ *     detached, train.py:280).
+ */
+typedef struct spml_head_args {
+  const float* e;               /* [n, dim]      cluster_embedding */
+  const float* el;              /* [n, dim_loc]  cluster_embedding_with_loc (nullable) */
+  const int64_t* seg;           /* [n] cluster_index (ids in [0, m)) */
+  const int64_t* bid;           /* [n] cluster_batch_index */
+  const int64_t* sem;           /* [n] cluster_semantic_label */
+  const int64_t* inst;          /* [n] cluster_instance_label */
+  const float* protos;          /* [m, dim]      prototype */
+  const float* protos_loc;      /* [m, dim_loc]  prototype_with_loc (nn_tags only) */
+  const int64_t* psem;          /* [m] */
+  const int64_t* pinst;         /* [m] nullable */
+  const int64_t* pbid;          /* [m] */
+  const int64_t* img_tags;      /* [tag_rows, img_tags_ld] */
+  const int64_t* ptags;         /* [m, ptags_ld] */
+  int64_t img_tags_ld, ptags_ld, tag_rows;
+  int64_t n, m, num_classes;
+  int64_t max_rows_per_group;   /* upper bound on the pixels of one image (0: n) */
+  int32_t dim, dim_loc;
+  int32_t tag_col0, tag_col1;
+  int32_t num_bank, max_groups;
+  uint32_t enable;
+  int32_t nn_tags, img_sim_on_plain, wide_tags;
+  float kappa_ann, kappa_occ, kappa_sim;
+  float weight_ann, weight_occ, weight_sim;
+  float nn_threshold, eps;
+  int32_t* status;              /* device word, nullable */
+  const float* bank_protos[SPML_MAX_BANK];
+  const float* bank_protos_loc[SPML_MAX_BANK];
+  const int64_t* bank_psem[SPML_MAX_BANK];
+  const int64_t* bank_pbid[SPML_MAX_BANK];
+  const int64_t* bank_tags[SPML_MAX_BANK];
+  int64_t bank_tags_ld[SPML_MAX_BANK];
+  int64_t bank_m[SPML_MAX_BANK];
+} spml_head_args;
+
+size_t spml_head_workspace_bytes(const spml_head_args* args);
+int spml_head_fwd(const spml_head_args* args, void* state, size_t state_bytes, float* out,
+                  void* stream);
+int spml_head_bwd(const spml_head_args* args, void* state, size_t state_bytes,
+                  const float* g_ann, const float* g_occ, const float* g_sim, float* de,
+                  float* del, float* dprotos, void* stream);
 
 #ifdef __cplusplus
 }

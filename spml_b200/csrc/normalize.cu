@@ -13,7 +13,10 @@ constexpr int kPackThreads = 256;
 
 __device__ __forceinline__ bool pixel_kept(const int64_t* labels, int has_ignore,
                                            int64_t ignore_index, int64_t pix) {
-  return !has_ignore || labels[pix] != ignore_index;
+  // has_ignore: 0 keeps everything, 1 drops label == ignore_index, 2 keeps label < ignore_index
+  if (!has_ignore) return true;
+  const int64_t v = labels[pix];
+  return has_ignore == 2 ? v < ignore_index : v != ignore_index;
 }
 
 // the ignore index may live on the device (generate_clusters passes labels.max() + 1)

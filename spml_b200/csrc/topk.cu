@@ -13,6 +13,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "internal.h"
 
 namespace cg = cooperative_groups;
 
@@ -22,13 +23,14 @@ constexpr int kTopkWarps = 8;
 constexpr int kTopkCols = 64;  // prototypes staged per step
 constexpr int kTopkCluster = 8;  // CTAs sharing one block of queries
 
-template <int KMAX, int QW>
+
+template <int KMAX, int QW, bool kExtra>
 __global__ void __launch_bounds__(kTopkWarps * 32, QW > 1 ? 2 : 1)
 topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p, int64_t m,
             int dim, const int64_t* __restrict__ qlab, const int64_t* __restrict__ plab,
             const uint8_t* __restrict__ qvalid, const uint8_t* __restrict__ pvalid, int k,
             int64_t* __restrict__ topk_labels, int64_t* __restrict__ topk_index,
-            int32_t* hit_count) {
+            int32_t* hit_count, TopkExtra x) {
   // A warp owns QW query rows: a prototype value read from shared memory feeds QW FMAs
   // (the kernel is bound by shared-memory reads, not by the FMAs).
   constexpr int kQ = kTopkWarps * QW;        // queries per CTA (and per cluster)
@@ -44,10 +46,12 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
   const int64_t row0 = (int64_t)(blockIdx.x / kTopkCluster) * kQ + warp * QW;
   bool active[QW];
   bool any = false;
+  int qg[QW];   // group ids (image indices) fit 32 bits
 #pragma unroll
   for (int i = 0; i < QW; ++i) {
     active[i] = row0 + i < nq && (!qvalid || qvalid[row0 + i]);
     any |= active[i];
+    qg[i] = (kExtra && x.qgroup && active[i]) ? (int)x.qgroup[row0 + i] : 0;
   }
   // fixed-capacity buffers: a block of padding rows (the same for the whole cluster)
   if (!__syncthreads_or(any)) return;
@@ -161,11 +165,13 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = lane + 32 * h;
-      const bool col_ok = j < cc && (!pvalid || pvalid[c0 + j]);
+      bool col_ok = j < cc && (!pvalid || pvalid[c0 + j]);
+      if (kExtra && col_ok && x.has_limit) col_ok = plab[c0 + j] < x.plab_limit;
+      const int pg = (kExtra && x.pgroup && col_ok) ? (int)x.pgroup[c0 + j] : 0;
 #pragma unroll
       for (int i = 0; i < QW; ++i) {
         const float v = acc[i][h];
-        if (col_ok && v > lv[i][KMAX - 1]) {
+        if (col_ok && (!kExtra || !x.pgroup || pg == qg[i]) && v > lv[i][KMAX - 1]) {
           // columns arrive in increasing index, so a strict '>' keeps the lowest index on ties
           lv[i][KMAX - 1] = v;
           li[i][KMAX - 1] = (int)(c0 + j);
@@ -242,6 +248,7 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
           const int64_t lab = found ? plab[bi] : -1;
           topk_labels[row * k + r] = lab;
           if (topk_index) topk_index[row * k + r] = found ? bi : -1;
+          if (kExtra && x.sim) x.sim[row * k + r] = found ? bv : -INFINITY;
           hits += found && lab == ql;
         }
       }
@@ -255,18 +262,16 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
 
 }  // namespace spml
 
-extern "C" {
+namespace spml {
 
-int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int dim,
-                      const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
-                      const uint8_t* pvalid, int k, int64_t* topk_labels, int64_t* topk_index,
-                      int32_t* hit_count, void* stream) {
-  using namespace spml;
+int topk_launch(const float* q, int64_t nq, const float* p, int64_t m, int dim,
+                const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
+                const uint8_t* pvalid, int k, int64_t* topk_labels, int64_t* topk_index,
+                int32_t* hit_count, const TopkExtra& extra, cudaStream_t st) {
   SPML_CHECK_ARG(nq >= 0 && m >= 0 && dim > 0 && k > 0 && hit_count, "topk_ranking: bad arguments");
   SPML_CHECK_SUPPORTED(k <= SPML_MAX_TOPK, "topk_ranking: k %d exceeds %d", k, SPML_MAX_TOPK);
   SPML_CHECK_SUPPORTED(dim <= 1024 && m < (1ll << 31), "topk_ranking: problem too large");
   SPML_CHECK_ARG(m >= k, "topk_ranking: fewer prototypes (%lld) than k (%d)", (long long)m, k);
-  cudaStream_t st = as_stream(stream);
   SPML_CUDA(cudaMemsetAsync(hit_count, 0, 2 * sizeof(int32_t), st));
   if (nq == 0) return SPML_OK;
   SPML_CHECK_ARG(q && p && qlab && plab && topk_labels, "topk_ranking: null pointer");
@@ -285,18 +290,96 @@ int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const bool extra_on = extra.qgroup || extra.pgroup || extra.has_limit || extra.sim;
+#define SPML_TOPK_LAUNCH(KMAXV, QWV, EXTRAV)                                                    \
+  do {                                                                                          \
+    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<KMAXV, QWV, EXTRAV>,                             \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    SPML_CUDA(cudaLaunchKernelEx(&cfg, topk_kernel<KMAXV, QWV, EXTRAV>, q, nq, p, m, dim, qlab, \
+                                 plab, qvalid, pvalid, k, topk_labels, topk_index, hit_count,   \
+                                 extra));                                                       \
+  } while (0)
   if (k <= 8) {
-    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    SPML_CUDA(cudaLaunchKernelEx(&cfg, topk_kernel<8, 4>, q, nq, p, m, dim, qlab, plab, qvalid,
-                                 pvalid, k, topk_labels, topk_index, hit_count));
+    if (extra_on) SPML_TOPK_LAUNCH(8, 4, true); else SPML_TOPK_LAUNCH(8, 4, false);
   } else {
-    SPML_CUDA(cudaFuncSetAttribute(topk_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    SPML_CUDA(cudaLaunchKernelEx(&cfg, topk_kernel<32, 1>, q, nq, p, m, dim, qlab, plab, qvalid,
-                                 pvalid, k, topk_labels, topk_index, hit_count));
+    if (extra_on) SPML_TOPK_LAUNCH(32, 1, true); else SPML_TOPK_LAUNCH(32, 1, false);
   }
+#undef SPML_TOPK_LAUNCH
   SPML_LAUNCH_CHECK("topk_kernel");
+  return SPML_OK;
+}
+
+// f3: tags[q, c] = 1 iff one of the retrieved prototypes of q has label c and is at least
+// `threshold` similar (models/utils.py:207-221).
+__global__ void nn_tags_kernel(const int64_t* __restrict__ labels, const float* __restrict__ sim,
+                               int64_t nq, int k, int num_classes, float threshold,
+                               int64_t* __restrict__ tags, int64_t* __restrict__ masks) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nq) return;
+  unsigned long long bits = 0;
+  for (int i = 0; i < k; ++i) {
+    const int64_t lab = labels[r * k + i];
+    if (lab >= 0 && lab < num_classes && lab < 64 && !(sim[r * k + i] < threshold))
+      bits |= 1ull << lab;
+  }
+  if (tags)
+    for (int c = 0; c < num_classes; ++c) tags[r * num_classes + c] = c < 64 ? (bits >> c) & 1ull : 0;
+  if (masks) masks[r] = (int64_t)bits;
+}
+
+}  // namespace spml
+
+extern "C" {
+
+int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int dim,
+                      const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
+                      const uint8_t* pvalid, int k, int64_t* topk_labels, int64_t* topk_index,
+                      int32_t* hit_count, void* stream) {
+  spml::TopkExtra none{};
+  return spml::topk_launch(q, nq, p, m, dim, qlab, plab, qvalid, pvalid, k, topk_labels,
+                           topk_index, hit_count, none, spml::as_stream(stream));
+}
+
+size_t spml_nn_multiset_labels_workspace_bytes(int64_t nq, int top_k) {
+  if (nq <= 0 || top_k <= 0) return 16;
+  return 16 + (size_t)nq * top_k * (sizeof(int64_t) + sizeof(float));
+}
+
+int spml_nn_multiset_labels(const float* q, int64_t nq, const float* p, int64_t m, int dim,
+                            const int64_t* plab, const int64_t* qgroup, const int64_t* pgroup,
+                            int num_classes, int top_k, float threshold, int64_t* tags,
+                            int64_t* masks, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  using namespace spml;
+  SPML_CHECK_ARG(nq >= 0 && m >= 0 && dim > 0 && top_k > 0 && num_classes > 0 && (tags || masks),
+                 "nn_multiset_labels: bad arguments");
+  SPML_CHECK_SUPPORTED(!masks || num_classes <= 64,
+                       "nn_multiset_labels: bit masks hold at most 64 classes");
+  if (nq == 0) return SPML_OK;
+  SPML_CHECK_ARG(q && p && plab && workspace, "nn_multiset_labels: null pointer");
+  const size_t need = spml_nn_multiset_labels_workspace_bytes(nq, top_k);
+  if (workspace_bytes < need) {
+    set_error("nn_multiset_labels: workspace %zu < %zu bytes", workspace_bytes, need);
+    return SPML_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* base = reinterpret_cast<char*>(workspace);
+  int32_t* hits = reinterpret_cast<int32_t*>(base);
+  int64_t* labels = reinterpret_cast<int64_t*>(base + 16);
+  float* sim = reinterpret_cast<float*>(base + 16 + (size_t)nq * top_k * sizeof(int64_t));
+  TopkExtra extra{};
+  extra.qgroup = qgroup;
+  extra.pgroup = pgroup;
+  extra.plab_limit = num_classes;
+  extra.has_limit = 1;
+  extra.sim = sim;
+  // the reference's torch.topk raises when there are fewer prototypes than top_k
+  int rc = topk_launch(q, nq, p, m, dim, plab /* query labels are unused */, plab, nullptr,
+                       nullptr, top_k, labels, nullptr, hits, extra, st);
+  if (rc != SPML_OK) return rc;
+  nn_tags_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(labels, sim, nq, top_k, num_classes,
+                                                              threshold, tags, masks);
+  SPML_LAUNCH_CHECK("nn_tags_kernel");
   return SPML_OK;
 }
 

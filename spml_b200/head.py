@@ -16,50 +16,80 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import model_utils, predictions, segsort_common
+from . import general_common, model_utils, predictions, segsort_common
 
 
 def generate_clusters(embeddings, semantic_labels, instance_labels, local_features,
                       label_divisor, semantic_ignore_index, num_clusters, iterations,
-                      batch_index_offset=None):
-  """spml/models/embeddings/resnet_deeplab.py:90-148 (labels already at the embedding
-  resolution).  The ignore id `labels.max() + 1` stays on the device."""
+                      batch_index_offset=None, densepose=False):
+  """spml/models/embeddings/resnet_deeplab.py:90-148 / resnet_pspnet.py:90-148 (labels already
+  at the embedding resolution).  The label packing (`sem * divisor + inst`, pixels with the
+  ignore label dropped) and the decoding of the kept pixels' labels happen inside the one
+  library call of segment_by_kmeans.  `densepose=True` adds the post-step of
+  resnet_pspnet_densepose.py:141-154: cluster_embedding_with_loc becomes
+  normalize(cat[0.1 * cluster_embedding, local features of the kept pixels])."""
   if semantic_labels is not None and instance_labels is not None:
-    labels = semantic_labels * label_divisor + instance_labels
-    ignore_index = labels.max() + 1
-    # torch.where, not masked_fill: a tensor fill value would cost a device->host read-back
-    labels = torch.where(semantic_labels == semantic_ignore_index, ignore_index, labels)
+    emb, emb_loc, _, cid, bid, sem, inst = segsort_common.segment_clusters(
+        embeddings, None, num_clusters, local_features=local_features, iterations=iterations,
+        batch_index_offset=batch_index_offset, semantic_labels=semantic_labels,
+        instance_labels=instance_labels, label_divisor=label_divisor,
+        semantic_ignore_index=semantic_ignore_index)
   else:
-    labels, ignore_index = None, None
-  emb, emb_loc, lab, cid, bid = segsort_common.segment_by_kmeans(
-      embeddings, labels, num_clusters, local_features=local_features,
-      ignore_index=ignore_index, iterations=iterations, batch_index_offset=batch_index_offset)
+    emb, emb_loc, lab, cid, bid = segsort_common.segment_by_kmeans(
+        embeddings, None, num_clusters, local_features=local_features, iterations=iterations,
+        batch_index_offset=batch_index_offset)
+    sem, inst = lab // label_divisor, lab % label_divisor
+  if densepose and local_features is not None:
+    loc = local_features.reshape(-1, local_features.shape[-1])
+    if semantic_labels is not None:
+      keep = (semantic_labels != semantic_ignore_index).view(-1).nonzero().view(-1)
+      loc = torch.index_select(loc, 0, keep)
+    emb_loc = general_common.normalize_embedding(torch.cat([emb * 0.1, loc], dim=-1))
   return {'cluster_embedding': emb, 'cluster_embedding_with_loc': emb_loc,
-          'cluster_semantic_label': lab // label_divisor,
-          'cluster_instance_label': lab % label_divisor,
+          'cluster_semantic_label': sem, 'cluster_instance_label': inst,
           'cluster_index': cid, 'cluster_batch_index': bid}
+
+
+def generate_clusters_method(densepose=False):
+  """A drop-in for the `generate_clusters` METHOD of the reference's embedding models
+  (ResnetDeeplab / ResnetPspnet, and the DensePose ResnetPspnet with densepose=True); it reads
+  the same four attributes of `self`."""
+  def method(self, embeddings, semantic_labels, instance_labels, local_features=None):
+    return generate_clusters(embeddings, semantic_labels, instance_labels, local_features,
+                             self.label_divisor, self.semantic_ignore_index,
+                             self.kmeans_num_clusters, self.kmeans_iterations,
+                             densepose=densepose)
+  method.__name__ = 'generate_clusters'
+  return method
 
 
 class ContrastiveHead(nn.Module):
 
-  def __init__(self, config, softmax_classifier=False):
+  def __init__(self, config, softmax_classifier=False, variant=None):
+    """`variant`: 'segsort' (predictions/segsort.py), 'softmax' (segsort_softmax.py, the
+    class train.py instantiates) or 'densepose' (resnet_pspnet_densepose.py clusters +
+    segsort_softmax_densepose.py, train_densepose.py:159-205)."""
     super(ContrastiveHead, self).__init__()
     self.config = config
-    self.predictor = (predictions.SegsortSoftmax(config) if softmax_classifier
-                      else predictions.Segsort(config))
+    self.variant = variant or ('softmax' if softmax_classifier else 'segsort')
+    self.predictor = {'segsort': predictions.Segsort, 'softmax': predictions.SegsortSoftmax,
+                      'densepose': predictions.SegsortSoftmaxDensepose}[self.variant](config)
     self.memory_bank_size = int(getattr(config.train, 'memory_bank_size', 0))
     self.memory_banks = {}
     self._last_targets = None
     self._last_batch = 0
 
   def forward(self, embedding, semantic_label, instance_label, semantic_tag,
-              local_feature=None):
+              local_feature=None, semantic_label_full=None):
+    """`semantic_label_full`: the full-resolution label map the classifier of the softmax
+    variants is trained on (targets['semantic_label']); default: `semantic_label`."""
     cfg = self.config
     datas = generate_clusters(
         embedding, semantic_label, instance_label, local_feature, cfg.network.label_divisor,
         cfg.dataset.semantic_ignore_index, cfg.network.kmeans_num_clusters,
         cfg.network.kmeans_iterations,
-        batch_index_offset=0)   # rank-local image indices: `semantic_tag` is this rank's
+        batch_index_offset=0,   # rank-local image indices: `semantic_tag` is this rank's
+        densepose=self.variant == 'densepose')
     (protos, protos_loc, psem, pinst, pbid, cids) = (
         model_utils.gather_clustering_and_update_prototypes(
             [datas['cluster_embedding']], [datas['cluster_embedding_with_loc']],
@@ -69,9 +99,12 @@ class ContrastiveHead(nn.Module):
     datas['embedding'] = embedding
     targets = {'prototype': protos[0], 'prototype_with_loc': protos_loc[0],
                'prototype_semantic_label': psem[0], 'prototype_instance_label': pinst[0],
-               'prototype_batch_index': pbid[0], 'semantic_tag': semantic_tag,
-               'semantic_label': semantic_label,
-               'prototype_semantic_tag': torch.index_select(semantic_tag, 0, pbid[0])}
+               'prototype_batch_index': pbid[0],
+               'semantic_label': semantic_label_full if semantic_label_full is not None
+                                 else semantic_label}
+    if self.variant != 'densepose':                 # train_densepose.py:189-199 (commented out)
+      targets['semantic_tag'] = semantic_tag
+      targets['prototype_semantic_tag'] = torch.index_select(semantic_tag, 0, pbid[0])
     targets.update(self.memory_banks)                                  # train.py:204-208
     out = self.predictor(datas, targets)
     losses = [out[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss')

@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from . import segsort_common
 
 
 def _cat_on(tensors, device):
@@ -34,7 +35,7 @@ def gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, clu
                        'tensors (no CPU path)')
   if anchor.index is None:
     anchor = torch.device('cuda', torch.cuda.current_device())
-  meta = getattr(cluster_indices[0], '_spml_meta', None) if len(cluster_indices) == 1 else None
+  meta = segsort_common.segment_meta(cluster_indices[0]) if len(cluster_indices) == 1 else None
 
   e = _cat_on(embeddings, anchor)
   el = _cat_on(embeddings_with_loc, anchor)
@@ -43,16 +44,15 @@ def gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, clu
   sem = _cat_on(semantic_labels, anchor)
   inst = _cat_on(instance_labels, anchor)
 
-  if meta is not None and meta.num_rows == cid.shape[0]:
+  if meta is not None and meta.num_rows == cid.shape[0] and cid.device == anchor:
     # ids straight from segment_by_kmeans are already the dense ranks of
-    # (image, cluster, label): both re-numberings of :95-108 are the identity,
-    # and the segment count is known -> no unique, no host sync.
-    m = meta.num_segments
+    # (image, cluster, label): both re-numberings of :95-108 are the identity, and the
+    # segment count is known -> no unique, no host sync, one library call.  The kernels
+    # check on the device that every segment carries one (batch, sem, inst) triple, i.e. that
+    # these really are the labels the ids were made from (ops.check_status reports it).
     new_cid = cid
-    p_bid = torch.empty(m, dtype=torch.int64, device=anchor).scatter_(0, cid, bid)
-    p_sem = torch.empty(m, dtype=torch.int64, device=anchor).scatter_(0, cid, sem)
-    p_inst = torch.empty(m, dtype=torch.int64, device=anchor).scatter_(0, cid, inst)
-    new_cid._spml_meta = meta
+    protos, protos_loc, p_sem, p_inst, p_bid = ops.GatherPrototypesFn.apply(
+        e, el, cid, bid, sem, inst, meta.num_segments)
   else:
     if cid.numel() == 0:
       raise RuntimeError('gather_clustering_and_update_prototypes: no pixels')
@@ -65,9 +65,8 @@ def gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, clu
     p_bid = plab // (div * div)
     p_sem = (plab % (div * div)) // div
     p_inst = plab % div
-
-  protos = ops.SegmentPrototypes.apply(e, new_cid, m)                                # :113-116
-  protos_loc = ops.SegmentPrototypes.apply(el, new_cid, m)
+    protos = ops.SegmentPrototypes.apply(e, new_cid, m)                              # :113-116
+    protos_loc = ops.SegmentPrototypes.apply(el, new_cid, m)
 
   if len(sections) == 1:
     split_cid = [new_cid]
@@ -87,19 +86,37 @@ def gather_and_update_datas(datas, anchor_device=None):
   return [gathered.to(d) for d in devices]
 
 
+def gather_multiset_labels_per_batch_by_nearest_neighbor(
+    embeddings, prototypes, semantic_prototype_labels, batch_embedding_labels,
+    batch_prototype_labels, num_classes=21, top_k=3, threshold=0.95, label_divisor=255):
+  """spml/models/utils.py:157-223: multi-hot [rows, num_classes] tags from each row's top_k
+  most similar prototypes of the same image that carry a class label (< num_classes) and are
+  at least `threshold` similar.  One top-k launch over the [rows, prototypes] similarities
+  (never materialised) instead of mm + where + topk + gathers; `label_divisor` is unused in
+  the reference too."""
+  return ops.nn_multiset_labels(embeddings.detach(), prototypes.detach(),
+                                semantic_prototype_labels, batch_embedding_labels,
+                                batch_prototype_labels, num_classes, top_k, threshold)
+
+
 def get_params(model, prefixs, suffixes, exclude=None):
-  """spml/models/utils.py:12-38 (host glue, unchanged semantics)."""
-  for name, module in model.named_modules():
-    for prefix in prefixs:
-      if name == prefix:
-        for n, p in module.named_parameters():
-          n = '.'.join([name, n])
-          if type(exclude) == list and n in exclude:
-            continue
-          if type(exclude) == str and exclude in n:
-            continue
-          for suffix in suffixes:
-            if ((n.split('.')[-1].startswith(suffix) or n.endswith(suffix))
-                and p.requires_grad):
-              yield p
-        break
+  """spml/models/utils.py:12-38: the trainable parameters of the sub-modules named in
+  `prefixs` whose leaf name starts with (or whose full name ends with) one of `suffixes`;
+  `exclude` is a list of full names or a substring."""
+  modules = dict(model.named_modules())
+  for prefix in prefixs:
+    module = modules.get(prefix)
+    if module is None:
+      continue
+    for leaf, param in module.named_parameters():
+      full = prefix + '.' + leaf
+      if isinstance(exclude, list) and full in exclude:
+        continue
+      if isinstance(exclude, str) and exclude in full:
+        continue
+      if not param.requires_grad:
+        continue
+      last = full.rsplit('.', 1)[-1]
+      for suffix in suffixes:      # one yield per matching suffix, like the reference's loop
+        if last.startswith(suffix) or full.endswith(suffix):
+          yield param

@@ -312,10 +312,10 @@ class SegsortLossFn(torch.autograd.Function):
     ws = _workspace(lib.spml_segsort_workspace_bytes(ctypes.byref(d)), dev)
     stats = torch.empty(max(problem.n_rows, 1), 3, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    _lib.PROFILE_TAG = ':' + problem.name if problem.name else ''
+    _lib.set_profile_tag(':' + problem.name if problem.name else '')
     call('spml_segsort_fwd', ctypes.byref(d), ptr(stats), None, ptr(loss), ptr(ws), ws.numel(),
          stream_of(emb))
-    _lib.PROFILE_TAG = ''
+    _lib.set_profile_tag('')
     ctx.save_for_backward(emb, protos, stats)
     ctx.problem = problem
     ctx.workspace = ws          # the bf16 operands prepared by the forward are re-used
@@ -339,10 +339,10 @@ class SegsortLossFn(torch.autograd.Function):
     if need_e or need_p:
       ws = ctx.workspace
       d.reserved |= 4
-      _lib.PROFILE_TAG = ':' + problem.name if problem.name else ''
+      _lib.set_profile_tag(':' + problem.name if problem.name else '')
       call('spml_segsort_bwd', ctypes.byref(d), ptr(stats), ptr(grad_loss), 0.0, ptr(demb),
            emb.shape[1], ptr(dprotos), ptr(ws), ws.numel(), stream_of(emb))
-      _lib.PROFILE_TAG = ''
+      _lib.set_profile_tag('')
     return demb, dprotos, None
 
 
@@ -380,3 +380,347 @@ def segment_labels(labels, batch, seg, rows_dev, divisor, num_classes, m_cap, de
        int(num_classes), int(m_cap), int(dead_label), ptr(sem), ptr(inst), ptr(keep), ptr(p_sem),
        ptr(p_inst), ptr(p_batch), ptr(p_live), ptr(overflow), stream_of(labels))
   return sem, inst, keep, p_sem, p_inst, p_batch, p_live
+
+
+# ------------------------------------------------------------------------------ f3
+
+
+def nn_multiset_labels(q, p, plab, qgroup, pgroup, num_classes, top_k, threshold):
+  """spml_nn_multiset_labels -> [rows, num_classes] int64 multi-hot tags."""
+  q = _f32c(q, 'nearest-neighbour tags(embeddings)')
+  p = _f32c(p, 'nearest-neighbour tags(prototypes)')
+  q2 = q.view(-1, q.shape[-1])
+  p2 = p.view(-1, q2.shape[1])
+  plab = _i64c(plab, 'nearest-neighbour tags(labels)').view(-1)
+  qgroup = _i64c(qgroup, 'nearest-neighbour tags').view(-1)
+  pgroup = _i64c(pgroup, 'nearest-neighbour tags').view(-1)
+  nq = q2.shape[0]
+  tags = torch.empty(nq, int(num_classes), dtype=torch.int64, device=q.device)
+  lib = _lib.load()
+  ws = _workspace(lib.spml_nn_multiset_labels_workspace_bytes(nq, int(top_k)), q.device)
+  call('spml_nn_multiset_labels', ptr(q2), nq, ptr(p2), p2.shape[0], q2.shape[1], ptr(plab),
+       ptr(qgroup), ptr(pgroup), int(num_classes), int(top_k), float(threshold), ptr(tags), None,
+       ptr(ws), ws.numel(), stream_of(q2))
+  return tags
+
+
+# ------------------------------------------------------------------------------ stage groups
+#
+# One C-ABI call per stage of the training step (csrc/pipeline.cu).  Each device has a small
+# status word the kernels OR error bits into; it is read together with the next step's row /
+# segment counts (the one host synchronisation of a step), so a violated precondition raises
+# one step late instead of costing a synchronisation of its own.
+
+STATUS_IMPURE_SEGMENT, STATUS_BAD_SEGMENT_ID, STATUS_TOO_MANY_IMAGES = 1, 2, 4
+_STATUS_TEXT = {
+    STATUS_IMPURE_SEGMENT: 'gather_clustering_and_update_prototypes: pixels of one segment carry '
+                           'different semantic / instance / batch labels (the ids were not '
+                           'produced from these labels)',
+    STATUS_BAD_SEGMENT_ID: 'a cluster index lies outside [0, number of prototypes)',
+    STATUS_TOO_MANY_IMAGES: 'img_sim: the pixels span more images than the batch size given',
+}
+_status_words = {}
+
+
+def status_word(device):
+  """int32[1] device tensor the stage kernels report violated preconditions into."""
+  key = device.index if device.index is not None else torch.cuda.current_device()
+  if key not in _status_words:
+    _status_words[key] = torch.zeros(1, dtype=torch.int32, device=device)
+  return _status_words[key]
+
+
+def raise_on_status(bits, device):
+  if bits:
+    status_word(device).zero_()
+    raise RuntimeError('spml_b200 (reported by an earlier, asynchronous call): ' + '; '.join(
+        text for bit, text in _STATUS_TEXT.items() if bits & bit))
+
+
+def check_status(device=None):
+  """Host-synchronising check of the status word (tests, end of a run)."""
+  device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+  raise_on_status(int(status_word(device)), device)
+
+
+class SegmentByKmeansFn(torch.autograd.Function):
+  """segment_by_kmeans (spml/utils/segsort/common.py:270-408) as ONE library call and one
+  host read-back (rows kept, segments, status).  Label packing of resnet_deeplab.py:112-117
+  happens inside the call when (sem, inst, divisor, semantic_ignore) are given instead of
+  `labels`.  `box` (a list) receives the sizes for the caller."""
+
+  @staticmethod
+  def forward(ctx, emb, loc, labels, sem, inst, divisor, semantic_ignore, ignore_index, seeds,
+              k_per_image, num_k, iterations, batch_index_offset, box):
+    emb = _f32c(emb, 'segment_by_kmeans(embeddings)')
+    B, D, H, W = emb.shape
+    n = H * W
+    cap = B * n
+    dev = emb.device
+    loc_ch, loc_bs, loc_c = 0, 0, None
+    if loc is not None:
+      if loc.dim() != 4 or loc.shape[1] != H or loc.shape[2] != W:
+        raise ValueError('local_features must be [batch, H, W, C]')
+      loc_ch = loc.shape[3]
+      if loc.stride(0) == 0 or loc.shape[0] == 1:
+        loc_c = _f32c(loc[0], 'local_features')
+      else:
+        loc_c, loc_bs = _f32c(loc, 'local_features'), n * loc_ch
+    DL = D + loc_ch
+    seeds_c = _i64c(seeds, 'cluster_indices')
+    seed_bs = 0 if seeds.dim() == 2 else n
+    lib = _lib.load()
+    fbuf = torch.empty(cap * (D + DL + 2), dtype=torch.float32, device=dev)
+    lbuf = torch.empty(cap * 5, dtype=torch.int64, device=dev)
+    head = (B + 2 + 3) // 4 * 4          # img_off [B + 1], num_segments [1]; keeps 16-byte alignment
+    ibuf = torch.empty(head + cap * 3, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.spml_segment_by_kmeans_workspace_bytes(B, n, DL, int(num_k),
+                                                               int(iterations)), dev)
+    a = _lib.ClusterArgs()
+    a.emb, a.loc, a.loc_batch_stride = emb.data_ptr(), (loc_c.data_ptr() if loc_ch else None), loc_bs
+    if labels is not None:
+      labels_c = _i64c(labels, 'segment_by_kmeans(labels)')
+      a.labels = labels_c.data_ptr()
+      a.has_ignore = int(ignore_index is not None)
+      if torch.is_tensor(ignore_index):      # stays on the device: no host sync
+        ignore_dev = ignore_index.to(device=dev, dtype=torch.int64).reshape(1)
+        a.ignore_index_dev = ignore_dev.data_ptr()
+      elif ignore_index is not None:
+        a.ignore_index = int(ignore_index)
+    else:
+      sem_c, inst_c = _i64c(sem, 'semantic_labels'), _i64c(inst, 'instance_labels')
+      a.sem, a.inst = sem_c.data_ptr(), inst_c.data_ptr()
+      a.semantic_ignore = int(semantic_ignore)
+    a.label_divisor = int(divisor) if divisor else 0
+    a.seeds, a.seed_batch_stride = seeds_c.data_ptr(), seed_bs
+    a.k_per_image = k_per_image.data_ptr() if k_per_image is not None else None
+    a.batch_index_offset = int(batch_index_offset)
+    a.batch, a.dim, a.n, a.loc_ch = B, D, n, loc_ch
+    a.num_clusters, a.iterations, a.eps = int(num_k), int(iterations), EPS
+    fp, lp, ip = fbuf.data_ptr(), lbuf.data_ptr(), ibuf.data_ptr()
+    a.e, a.el = fp, fp + 4 * cap * D
+    a.nx, a.nc = fp + 4 * cap * (D + DL), fp + 4 * cap * (D + DL + 1)
+    a.labels_out, a.batch_out, a.segment_ids = lp, lp + 8 * cap, lp + 16 * cap
+    if divisor:
+      a.sem_out, a.inst_out = lp + 24 * cap, lp + 32 * cap
+    a.img_off, a.num_segments = ip, ip + 4 * (B + 1)
+    a.dst = ip + 4 * head
+    a.kmeans_labels, a.seed_out = ip + 4 * (head + cap), ip + 4 * (head + 2 * cap)
+    status = status_word(dev)
+    call('spml_segment_by_kmeans', ctypes.byref(a), ptr(ws), ws.numel(), stream_of(emb))
+    # the one host synchronisation of the step: rows kept, segments, pending error bits
+    rows, segments, bits = torch.cat([ibuf[B:B + 2], status]).tolist()
+    raise_on_status(bits, dev)
+    e = torch.as_strided(fbuf, (rows, D), (D, 1), 0)
+    el = torch.as_strided(fbuf, (rows, DL), (DL, 1), cap * D)
+    nx = torch.as_strided(fbuf, (rows,), (1,), cap * (D + DL))
+    nc = torch.as_strided(fbuf, (rows,), (1,), cap * (D + DL + 1))
+    lab, bid, cid = lbuf[:rows], lbuf[cap:cap + rows], lbuf[2 * cap:2 * cap + rows]
+    dst = ibuf[head:head + cap]
+    outs = [e, el, lab, cid, bid]
+    if divisor:
+      outs += [lbuf[3 * cap:3 * cap + rows], lbuf[4 * cap:4 * cap + rows]]
+    ctx.save_for_backward(e, el, nx, nc, dst)
+    ctx.dims = (B, D, loc_ch, H, W)
+    ctx.mark_non_differentiable(*outs[2:])
+    box.append((rows, segments, ibuf[:B + 1]))
+    return tuple(outs)
+
+  @staticmethod
+  def backward(ctx, de, del_, *_):
+    e, el, nx, nc, dst = ctx.saved_tensors
+    B, D, loc_ch, H, W = ctx.dims
+    demb = torch.empty(B, D, H, W, dtype=torch.float32, device=e.device)
+    de = _f32c(de, 'd(cluster_embedding)') if de is not None else None
+    del_ = _f32c(del_, 'd(cluster_embedding_with_loc)') if del_ is not None else None
+    call('spml_normalize_pack_bwd', ptr(de), ptr(del_), ptr(e), ptr(el), ptr(nx), ptr(nc),
+         ptr(dst), B, D, loc_ch, H * W, EPS, ptr(demb), stream_of(e))
+    return (demb,) + (None,) * 13
+
+
+class GatherPrototypesFn(torch.autograd.Function):
+  """spml/models/utils.py:100-116 for ids fresh from segment_by_kmeans: per-segment labels and
+  the two prototype sets in one library call."""
+
+  @staticmethod
+  def forward(ctx, e, el, cid, bid, sem, inst, m):
+    e = _f32c(e, 'gather(embeddings)')
+    el = _f32c(el, 'gather(embeddings_with_loc)')
+    rows, D, DL = e.shape[0], e.shape[1], el.shape[1]
+    dev = e.device
+    m = int(m)
+    lib = _lib.load()
+    fbuf = torch.empty(m * (D + DL + 2), dtype=torch.float32, device=dev)
+    plab = torch.empty(3, m, dtype=torch.int64, device=dev)
+    ws = _workspace(lib.spml_gather_prototypes_workspace_bytes(m, D, DL), dev)
+    protos = torch.as_strided(fbuf, (m, D), (D, 1), 0)
+    protos_loc = torch.as_strided(fbuf, (m, DL), (DL, 1), m * D)
+    norms = torch.as_strided(fbuf, (m,), (1,), m * (D + DL))
+    norms_loc = torch.as_strided(fbuf, (m,), (1,), m * (D + DL + 1))
+    cid, bid = _i64c(cid, 'cluster_indices'), _i64c(bid, 'batch_indices')
+    sem, inst = _i64c(sem, 'semantic_labels'), _i64c(inst, 'instance_labels')
+    call('spml_gather_prototypes_fwd', ptr(e), ptr(el), rows, D, DL, ptr(cid), ptr(bid), ptr(sem),
+         ptr(inst), m, EPS, ptr(protos), ptr(protos_loc), ptr(norms), ptr(norms_loc),
+         ptr(plab[0]), ptr(plab[1]), ptr(plab[2]), ptr(status_word(dev)), ptr(ws), ws.numel(),
+         stream_of(e))
+    ctx.save_for_backward(protos, protos_loc, norms, norms_loc, cid)
+    p_sem, p_inst, p_bid = plab[0], plab[1], plab[2]
+    ctx.mark_non_differentiable(p_sem, p_inst, p_bid)
+    return protos, protos_loc, p_sem, p_inst, p_bid
+
+  @staticmethod
+  def backward(ctx, dp, dpl, *_):
+    protos, protos_loc, norms, norms_loc, cid = ctx.saved_tensors
+    rows, m = cid.shape[0], protos.shape[0]
+    D, DL = protos.shape[1], protos_loc.shape[1]
+    dev = protos.device
+    de = del_ = None
+    if dp is not None:
+      dp = _f32c(dp, 'd(prototypes)')
+      de = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    if dpl is not None:
+      dpl = _f32c(dpl, 'd(prototypes_with_loc)')
+      del_ = torch.empty(rows, DL, dtype=torch.float32, device=dev)
+    if dp is not None or dpl is not None:
+      call('spml_gather_prototypes_bwd', ptr(dp), ptr(dpl), ptr(protos), ptr(protos_loc),
+           ptr(norms), ptr(norms_loc), ptr(cid), rows, D, DL, m, EPS, ptr(de), ptr(del_),
+           stream_of(protos))
+    return de, del_, None, None, None, None, None
+
+
+ENABLE_ANN, ENABLE_OCC, ENABLE_SIM, ENABLE_ACC = 1, 2, 4, 8
+
+
+class HeadSpec:
+  """The non-differentiable inputs of one spml_head_fwd / spml_head_bwd pair: labels, tags,
+  memory bank, switches.  Keeps every tensor whose address is in the argument struct alive."""
+
+  def __init__(self, cid, bid, sem, inst, psem, pinst, pbid, num_classes, enable, kappas, weights,
+               max_groups, max_rows_per_group=0, img_tags=None, ptags=None, tag_cols=(0, 0),
+               bank=(), nn_tags=False, img_sim_on_plain=False, protos_loc=None,
+               nn_threshold=0.95):
+    self.keep = []
+
+    def i64(t, name):
+      if t is None:
+        return None
+      t = _i64c(t, name)
+      self.keep.append(t)
+      return t
+
+    def f32(t, name):
+      if t is None:
+        return None
+      t = _f32c(t.detach(), name)
+      self.keep.append(t)
+      return t
+
+    def tags2d(t, name):
+      t = i64(t, name)
+      if t.dim() != 2 or t.stride(1) != 1:
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+        self.keep.append(t)
+      return t
+
+    a = _lib.HeadArgs()
+    self.args = a
+    self.cid = i64(cid, 'cluster_index').view(-1)
+    a.seg = self.cid.data_ptr()
+    a.n = self.cid.shape[0]
+    for field, t, name in (('bid', bid, 'cluster_batch_index'),
+                           ('sem', sem, 'cluster_semantic_label'),
+                           ('inst', inst, 'cluster_instance_label'),
+                           ('psem', psem, 'prototype_semantic_label'),
+                           ('pinst', pinst, 'prototype_instance_label'),
+                           ('pbid', pbid, 'prototype_batch_index')):
+      t = i64(t, name)
+      setattr(a, field, t.data_ptr() if t is not None else None)
+    a.m = psem.shape[0]
+    a.num_classes = int(num_classes)
+    a.enable = int(enable)
+    a.kappa_ann, a.kappa_occ, a.kappa_sim = [float(k or 0.0) for k in kappas]
+    a.weight_ann, a.weight_occ, a.weight_sim = [float(w or 0.0) for w in weights]
+    a.max_groups = max(1, int(max_groups))
+    a.max_rows_per_group = int(max_rows_per_group)
+    a.nn_tags, a.img_sim_on_plain = int(nn_tags), int(img_sim_on_plain)
+    a.nn_threshold, a.eps = float(nn_threshold), EPS
+    if enable & ENABLE_OCC:
+      if nn_tags:
+        t = f32(protos_loc, 'prototype_with_loc')
+        a.protos_loc, a.dim_loc = t.data_ptr(), t.shape[1]
+        a.wide_tags = int(num_classes > 32)
+      else:
+        it, pt = tags2d(img_tags, 'semantic_tag'), tags2d(ptags, 'prototype_semantic_tag')
+        a.img_tags, a.img_tags_ld, a.tag_rows = it.data_ptr(), it.stride(0), it.shape[0]
+        a.ptags, a.ptags_ld = pt.data_ptr(), pt.stride(0)
+        a.tag_col0, a.tag_col1 = int(tag_cols[0]), int(tag_cols[1])
+        if tag_cols[1] - tag_cols[0] > 64 or tag_cols[1] > it.shape[1]:
+          raise ValueError('image tags: at most 64 tag columns inside the tag matrix')
+        a.wide_tags = int(tag_cols[1] - tag_cols[0] > 32)
+    if len(bank) > _lib.MAX_BANK:
+      raise ValueError('memory bank: at most %d entries per call' % _lib.MAX_BANK)
+    a.num_bank = len(bank)
+    for i, entry in enumerate(bank):
+      bp = f32(entry['prototype'], 'memory_prototype')
+      bs = i64(entry['semantic_label'], 'memory_prototype_semantic_label')
+      a.bank_protos[i], a.bank_psem[i], a.bank_m[i] = bp.data_ptr(), bs.data_ptr(), bp.shape[0]
+      if enable & ENABLE_OCC:
+        if nn_tags:
+          bl = f32(entry['prototype_with_loc'], 'memory_prototype_with_loc')
+          bb = i64(entry['batch_index'], 'memory_prototype_batch_index')
+          a.bank_protos_loc[i], a.bank_pbid[i] = bl.data_ptr(), bb.data_ptr()
+        else:
+          bt = tags2d(entry['semantic_tag'], 'memory_prototype_semantic_tag')
+          a.bank_tags[i], a.bank_tags_ld[i] = bt.data_ptr(), bt.stride(0)
+
+
+class HeadLossFn(torch.autograd.Function):
+  """Everything of Segsort*.losses() but the conv classifier, forward and backward, as one
+  library call each.  Returns four 0-dim tensors: weighted sem_ann, sem_occ, img_sim and the
+  top-5 accuracy (entries of disabled losses are 0)."""
+
+  @staticmethod
+  def forward(ctx, e, el, protos, spec):
+    e = _f32c(e, 'cluster_embedding')
+    protos = _f32c(protos, 'prototype')
+    a = spec.args
+    dev = e.device
+    a.e, a.dim = e.data_ptr(), e.shape[1]
+    if el is not None:
+      el = _f32c(el, 'cluster_embedding_with_loc')
+      a.el, a.dim_loc = el.data_ptr(), el.shape[1]
+    a.protos = protos.data_ptr()
+    if e.shape[0] != a.n or protos.shape[0] != a.m:
+      raise ValueError('embeddings / prototypes disagree with their label vectors')
+    a.status = status_word(dev).data_ptr()
+    lib = _lib.load()
+    state = _workspace(lib.spml_head_workspace_bytes(ctypes.byref(a)), dev)
+    out = torch.empty(4, dtype=torch.float32, device=dev)
+    call('spml_head_fwd', ctypes.byref(a), ptr(state), state.numel(), ptr(out), stream_of(e))
+    ctx.spec, ctx.state = spec, state
+    ctx.save_for_backward(e, el, protos)
+    ctx.set_materialize_grads(False)
+    sem_ann, sem_occ, img_sim, acc = out.unbind(0)
+    ctx.mark_non_differentiable(acc)
+    return sem_ann, sem_occ, img_sim, acc
+
+  @staticmethod
+  def backward(ctx, g_ann, g_occ, g_sim, _g_acc):
+    e, el, protos = ctx.saved_tensors
+    spec, state = ctx.spec, ctx.state
+    a = spec.args
+    gs = [None if g is None else (g if g.dtype == torch.float32 else g.float())
+          for g in (g_ann, g_occ, g_sim)]
+    if all(g is None for g in gs):
+      return None, None, None, None
+    need_e, need_el, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+    sim_on_el = bool(a.enable & ENABLE_SIM) and not a.img_sim_on_plain
+    de = torch.empty_like(e)
+    del_ = torch.empty_like(el) if (el is not None and sim_on_el) else None
+    dprotos = torch.empty_like(protos) if need_p else None
+    call('spml_head_bwd', ctypes.byref(a), ptr(state), state.numel(), ptr(gs[0]), ptr(gs[1]),
+         ptr(gs[2]),
+         ptr(de), ptr(del_), ptr(dprotos), stream_of(e))
+    if el is not None and del_ is None and need_el:
+      del_ = torch.zeros_like(el)
+    return (de if need_e else None), (del_ if need_el else None), dprotos, None

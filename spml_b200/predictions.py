@@ -1,19 +1,27 @@
-"""Drop-in replacements for spml/models/predictions/segsort.py and segsort_softmax.py:
-the operator API boundary of the contrastive head.
+"""Drop-in replacements for spml/models/predictions/segsort.py, segsort_softmax.py and
+segsort_softmax_densepose.py: the operator API boundary of the contrastive head.
 
-`segsort(config)` / `segsort_softmax(config)` return nn.Modules with the reference's
-`forward(datas, targets=None, with_loss=True, with_prediction=False)` contract and
-the same output keys (sem_ann_loss, sem_occ_loss, img_sim_loss, accuracy).  The
-three losses run as one fused launch each (forward) instead of the reference's
-index_select copies and per-image Python loop:
+`segsort(config)` / `segsort_softmax(config)` / `segsort_softmax_densepose(config)` return
+nn.Modules with the reference's `forward(datas, targets=None, with_loss=True,
+with_prediction=False)` contract and the same output keys (sem_ann_loss, sem_occ_loss,
+img_sim_loss, accuracy).  Everything of `losses()` except the conv classifier of the softmax
+variants is ONE library call forward (spml_head_fwd) and one backward (spml_head_bwd):
 
-  sem_ann  SegSort over labelled pixels x labelled prototypes (+ memory bank);
-           the filters of segsort.py:184-201 become a device-side row list and a
-           column mask, nothing is copied or re-numbered.
-  sem_occ  SetSegSort over all pixels x all prototypes with 20-bit image-tag masks
-           instead of the [N, 20] x [20, M] float GEMM of loss.py:107-109.
-  img_sim  the per-image loop of segsort.py:220-240 as ONE grouped launch: rows are
-           grouped by image and each group only sees its own image's prototypes.
+  sem_ann  SegSort over labelled pixels x labelled prototypes (+ memory bank); the filters of
+           segsort.py:184-201 are a device-side row list and a column mask, nothing is copied
+           or re-numbered.
+  sem_occ  SetSegSort over all pixels x all prototypes with tag bit masks instead of the
+           [N, C] x [C, M] float GEMM of loss.py:107-109.  Tags are the image tags (VOC) or,
+           in the DensePose head, the class of each prototype's nearest labelled prototype of
+           the same image (segsort_softmax_densepose.py:174-191).
+  img_sim  the per-image loop of segsort.py:220-240 as one grouped launch: rows are grouped by
+           image and each group only sees its own image's prototypes.
+  accuracy top-5 retrieval among all prototypes (segsort.py:212-217).
+
+Preconditions shared with the reference's data flow (train.py:167-211), checked on the device
+where noted: `cluster_index` are ids in [0, #prototypes) whose pixels all carry one instance
+label (checked, reported through ops.check_status); pixels and prototypes are ordered by image
+(what segment_by_kmeans / gather_clustering_and_update_prototypes return).
 """
 
 from __future__ import annotations
@@ -22,9 +30,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
 from . import ops
-from . import model_utils
 from . import segsort_eval
 
 
@@ -37,26 +43,31 @@ def _construct_loss(loss_types, concentration):
   raise KeyError('Unsupported loss types: {:s}'.format(loss_types))
 
 
-def _row_groups(batch_indices, proto_batch_indices, max_groups):
-  """Row / column offsets of the per-image groups.  Pixels and prototypes are both
-  sorted by image (segment ids are ranks of (image, cluster, label)), so every
-  image is one contiguous range of rows and of prototype columns."""
-  dev = batch_indices.device
-  base = torch.minimum(batch_indices.min(), proto_batch_indices.min())
-  rel = (batch_indices - base).clamp_(0, max_groups - 1)
-  prel = (proto_batch_indices - base).clamp_(0, max_groups - 1)
-  rows = torch.zeros(max_groups, dtype=torch.int32, device=dev)
-  rows.scatter_add_(0, rel, torch.ones_like(rel, dtype=torch.int32))
-  cols = torch.zeros(max_groups, dtype=torch.int32, device=dev)
-  cols.scatter_add_(0, prel, torch.ones_like(prel, dtype=torch.int32))
-  zero = torch.zeros(1, dtype=torch.int32, device=dev)
-  group_off = torch.cat([zero, torch.cumsum(rows, 0, dtype=torch.int32)])
-  col_off = torch.cat([zero, torch.cumsum(cols, 0, dtype=torch.int32)])
-  return group_off, col_off
+def _bank_entries(targets, with_tags, with_loc):
+  """The memory-bank lists of train.py:204-208 as per-step entries, or [] when the
+  reference would skip the bank (one of the lists it tests is missing / empty)."""
+  protos = targets.get('memory_prototype', [])
+  sems = targets.get('memory_prototype_semantic_label', [])
+  bids = targets.get('memory_prototype_batch_index', [])
+  tags = targets.get('memory_prototype_semantic_tag', [])
+  locs = targets.get('memory_prototype_with_loc', [])
+  if not (protos and sems and bids) or (with_tags and not tags):
+    return []
+  entries = []
+  for i in range(len(protos)):
+    entry = {'prototype': protos[i], 'semantic_label': sems[i], 'batch_index': bids[i]}
+    if with_tags:
+      entry['semantic_tag'] = tags[i]
+    if with_loc:
+      entry['prototype_with_loc'] = locs[i]
+    entries.append(entry)
+  return entries
 
 
 class Segsort(nn.Module):
   """spml/models/predictions/segsort.py:15-283 (non-parametric predictor)."""
+
+  densepose = False
 
   def __init__(self, config):
     super(Segsort, self).__init__()
@@ -99,71 +110,47 @@ class Segsort(nn.Module):
 
   # ----------------------------------------------------------------------------
   def _contrastive_losses(self, datas, targets):
+    """Returns (sem_ann, sem_occ, img_sim, accuracy); sem_ann is already weighted."""
     C = self.num_classes
-    sem_ann_loss = sem_occ_loss = img_sim_loss = sem_ann_acc = None
-
-    if self.sem_ann_concentration is not None or self.sem_occ_concentration is not None:
-      cid = datas['cluster_index']
-      emb = datas['cluster_embedding']
-      sem = datas['cluster_semantic_label']
+    use_ann = self.sem_ann_concentration is not None
+    use_occ = self.sem_occ_concentration is not None
+    use_sim = self.img_sim_concentration is not None
+    if not (use_ann or use_occ or use_sim):
+      return None, None, None, None
+    contrast = use_ann or use_occ
+    enable = ((ops.ENABLE_ANN if use_ann else 0) | (ops.ENABLE_OCC if use_occ else 0) |
+              (ops.ENABLE_SIM if use_sim else 0) | (ops.ENABLE_ACC if contrast else 0))
+    densepose = self.densepose
+    cid = datas['cluster_index']
+    e = datas['cluster_embedding']
+    el = None if densepose else (datas['cluster_embedding_with_loc'] if use_sim else None)
+    bank = _bank_entries(targets, with_tags=not densepose, with_loc=densepose) if contrast else []
+    img_tags = ptags = protos_loc = None
+    if use_occ and not densepose:
+      img_tags, ptags = targets['semantic_tag'], targets['prototype_semantic_tag']
+    if use_occ and densepose:
+      protos_loc = targets['prototype_with_loc']
+    # upper bounds the grouped img_sim launch is sized with
+    emb_map = datas.get('embedding', None)
+    if emb_map is not None:
+      groups, rows_per_group = emb_map.shape[0], emb_map.shape[2] * emb_map.shape[3]
+    elif targets.get('semantic_tag', None) is not None:
+      groups, rows_per_group = targets['semantic_tag'].shape[0], 0
+    else:
       bid = datas['cluster_batch_index']
-      protos = targets['prototype']
-      psem = targets['prototype_semantic_label']
-      tags_img = targets['semantic_tag']
-      ptags = targets['prototype_semantic_tag']
-
-      mem_p = targets.get('memory_prototype', [])
-      mem_s = targets.get('memory_prototype_semantic_label', [])
-      mem_b = targets.get('memory_prototype_batch_index', [])
-      mem_t = targets.get('memory_prototype_semantic_tag', [])
-      # image-tag bit masks: columns 1..C-1 of the 256-wide presence vectors
-      # (segsort.py:146-150); one mask per image, gathered per pixel / prototype
-      pix_mask = torch.index_select(ops.pack_tags(tags_img[:, 1:C]), 0, bid)
-      proto_mask = ops.pack_tags(ptags[:, 1:C])
-      if mem_p and mem_s and mem_t and mem_b:                              # :153-182
-        protos = torch.cat([protos] + list(mem_p), dim=0)
-        psem = torch.cat([psem] + list(mem_s), dim=0)
-        proto_mask = torch.cat([proto_mask] + [ops.pack_tags(t[:, 1:C]) for t in mem_t], dim=0)
-
-      n = emb.shape[0]
-      if self.sem_ann_concentration is not None:
-        # :184-201 labelled pixels x labelled prototypes, without copies
-        keep = (sem < C).to(torch.int64).view(1, n)
-        _, rows, off = ops.valid_scan(keep, 0, 1, n, want_src=True)
-        problem = ops.SegsortProblem(
-            sem, cid, psem, self.sem_ann_concentration, _lib.MODE_CLASS,
-            row_index=rows, group_off=off, num_groups=1, n_rows=n, max_rows_per_group=n,
-            proto_valid=(psem < C))
-        sem_ann_loss = ops.SegsortLossFn.apply(emb, protos, problem) * self.sem_ann_loss_weight
-      if self.sem_occ_concentration is not None:
-        problem = ops.SegsortProblem(pix_mask, cid, proto_mask, self.sem_occ_concentration,
-                                     _lib.MODE_TAGS)
-        sem_occ_loss = ops.SegsortLossFn.apply(emb, protos, problem) * self.sem_occ_loss_weight
-      sem_ann_acc, _ = segsort_eval.top_k_ranking(protos, psem, protos, psem, 5)   # :212-217
-
-    if self.img_sim_concentration is not None:                              # :220-240
-      cid = datas['cluster_index']
-      emb_loc = datas['cluster_embedding_with_loc']
-      inst = datas['cluster_instance_label']
-      bid = datas['cluster_batch_index']
-      pbid = targets['prototype_batch_index']
-      m = pbid.shape[0]
-      n = emb_loc.shape[0]
-      # per-image prototypes of the location-augmented embeddings == the rows of one
-      # batched segment-prototype launch (each segment lives in exactly one image)
-      protos_loc = ops.SegmentPrototypes.apply(emb_loc, cid, m)
-      pinst = targets.get('prototype_instance_label', None)
-      if pinst is None:
-        pinst = torch.zeros(m, dtype=torch.int64, device=cid.device).scatter_(0, cid, inst)
-      groups = int(targets['semantic_tag'].shape[0])
-      group_off, col_off = _row_groups(bid, pbid, groups)
-      problem = ops.SegsortProblem(
-          inst, cid, pinst, self.img_sim_concentration, _lib.MODE_CLASS,
-          reduction=_lib.REDUCE_GROUP_MEAN, group_off=group_off, col_off=col_off,
-          num_groups=groups, n_rows=n, max_rows_per_group=n)
-      img_sim_loss = ops.SegsortLossFn.apply(emb_loc, protos_loc, problem) * self.img_sim_loss_weight
-
-    return sem_ann_loss, sem_occ_loss, img_sim_loss, sem_ann_acc
+      groups, rows_per_group = int(bid[-1] - bid[0]) + 1, 0            # host sync
+    spec = ops.HeadSpec(
+        cid, datas['cluster_batch_index'], datas['cluster_semantic_label'],
+        datas['cluster_instance_label'], targets['prototype_semantic_label'], None,
+        targets['prototype_batch_index'], C, enable,
+        (self.sem_ann_concentration, self.sem_occ_concentration, self.img_sim_concentration),
+        (self.sem_ann_loss_weight, self.sem_occ_loss_weight, self.img_sim_loss_weight),
+        max_groups=groups, max_rows_per_group=rows_per_group, img_tags=img_tags, ptags=ptags,
+        tag_cols=(0, C) if densepose else (1, C), bank=bank, nn_tags=densepose,
+        img_sim_on_plain=densepose, protos_loc=protos_loc)
+    sem_ann, sem_occ, img_sim, acc = ops.HeadLossFn.apply(e, el, targets['prototype'], spec)
+    return (sem_ann if use_ann else None, sem_occ if use_occ else None,
+            img_sim if use_sim else None, acc if contrast else None)
 
   def losses(self, datas, targets={}):
     """segsort.py:127-243."""
@@ -186,10 +173,10 @@ class Segsort(nn.Module):
 
 
 class SegsortSoftmax(Segsort):
-  """spml/models/predictions/segsort_softmax.py:15-290: the same contrastive head
-  plus a 2-conv softmax classifier on DETACHED, L2-normalised embeddings whose
-  cross-entropy is added to sem_ann_loss before weighting (:111-131,196-202).
-  The classifier is ordinary cuDNN work and stays torch.nn."""
+  """spml/models/predictions/segsort_softmax.py:15-290: the same contrastive head plus a
+  2-conv softmax classifier on DETACHED, channel-normalised embeddings whose cross-entropy
+  is added to sem_ann_loss before the weighting (:111-131,196-202).  The classifier is
+  ordinary cuDNN work and stays torch.nn (state-dict compatible with the reference's)."""
 
   def __init__(self, config):
     super(SegsortSoftmax, self).__init__(config)
@@ -202,25 +189,25 @@ class SegsortSoftmax(Segsort):
         nn.Conv2d(dim * 2, config.dataset.num_classes, kernel_size=1, stride=1, bias=True))
     self.softmax_loss = nn.CrossEntropyLoss(ignore_index=config.dataset.semantic_ignore_index)
 
+  def _logits(self, emb):
+    emb = emb / torch.norm(emb, dim=1, keepdim=True)
+    return self.semantic_classifier(emb)
+
   def predictions(self, datas, targets={}):
     """segsort_softmax.py:88-101."""
-    emb = datas['embedding']
-    emb = emb / torch.norm(emb, dim=1, keepdim=True)
-    logits = self.semantic_classifier(emb)
+    logits = self._logits(datas['embedding'])
     return torch.argmax(logits, dim=1), logits
 
   def losses(self, datas, targets={}):
-    """segsort_softmax.py:103-242."""
-    emb = datas['embedding'].detach()
-    emb = emb / torch.norm(emb, dim=1, keepdim=True)
-    logits = self.semantic_classifier(emb)
+    """segsort_softmax.py:103-242 / segsort_softmax_densepose.py:104-254."""
+    logits = self._logits(datas['embedding'].detach())
     labels = targets.get('semantic_label', None)
     logits = F.interpolate(logits, size=labels.shape[-2:], mode='bilinear')
     labels = labels.masked_fill(labels >= self.num_classes, self.semantic_ignore_index)
-    ce = self.softmax_loss(logits, labels.squeeze_(1).long())
+    ce = self.softmax_loss(logits, labels.squeeze(1).long())
     sem_ann, sem_occ, img_sim, acc = self._contrastive_losses(datas, targets)
-    if self.sem_ann_concentration is not None:
-      # (ce + segsort) * weight, as `sem_ann_loss += ...; sem_ann_loss *= weight`
+    if sem_ann is not None:
+      # `sem_ann_loss += segsort; sem_ann_loss *= weight` with the SegSort term already weighted
       sem_ann = ce * self.sem_ann_loss_weight + sem_ann
     else:
       sem_ann = ce
@@ -239,13 +226,29 @@ class SegsortSoftmax(Segsort):
     return outputs
 
   def get_params_lr(self):
-    """segsort_softmax.py:270-290."""
-    return [
-        {'params': [n for n in model_utils.get_params(self, ['semantic_classifier'], ['weight'])],
-         'lr': 10},
-        {'params': [n for n in model_utils.get_params(self, ['semantic_classifier'], ['bias'])],
-         'lr': 20, 'weight_decay': 0},
-    ]
+    """segsort_softmax.py:270-290: weights of the classifier at 10x, biases at 20x the base
+    learning rate and without weight decay."""
+    weights, biases = [], []
+    for name, p in self.semantic_classifier.named_parameters():
+      if not p.requires_grad:
+        continue
+      leaf = name.split('.')[-1]
+      if leaf.startswith('weight'):
+        weights.append(p)
+      elif leaf.startswith('bias'):
+        biases.append(p)
+    return [{'params': weights, 'lr': 10}, {'params': biases, 'lr': 20, 'weight_decay': 0}]
+
+
+class SegsortSoftmaxDensepose(SegsortSoftmax):
+  """spml/models/predictions/segsort_softmax_densepose.py:16-301 (there also named
+  `SegsortSoftmax`).  Differences from the VOC head, all inside the one library call:
+  prototype tag sets come from a same-image 1-NN over `prototype_with_loc` (threshold 0.95,
+  a prototype without a labelled neighbour gets every tag, :174-191), pixels inherit their
+  segment's tags, img_sim runs on `cluster_embedding` (:232-250) and the memory bank needs
+  no tag list (:158-172)."""
+
+  densepose = True
 
 
 def segsort(config):
@@ -256,3 +259,8 @@ def segsort(config):
 def segsort_softmax(config):
   """spml/models/predictions/segsort_softmax.py:293-295 (there also named `segsort`)."""
   return SegsortSoftmax(config)
+
+
+def segsort_softmax_densepose(config):
+  """spml/models/predictions/segsort_softmax_densepose.py:298-301 (there named `segsort`)."""
+  return SegsortSoftmaxDensepose(config)

@@ -6,6 +6,8 @@ reference module.  Every function needs CUDA tensors; there is no CPU path.
 
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -13,10 +15,8 @@ from . import general_common as common_utils
 
 
 class SegmentMeta:
-  """What segment_by_kmeans already knows about its result.  It rides on the
-  returned `cluster_indices` tensor (attribute `_spml_meta`) so that
-  gather_clustering_and_update_prototypes and the losses need no further host
-  synchronisation; code that ignores it loses nothing."""
+  """What segment_by_kmeans knows about a result it returned: the ids are already the dense
+  ranks of (image, cluster, label), and how many there are."""
 
   def __init__(self, num_segments, num_rows, img_off, batch, batch_index_offset):
     self.num_segments = num_segments    # M: distinct (image, cluster, label)
@@ -24,6 +24,27 @@ class SegmentMeta:
     self.img_off = img_off              # int32 [batch + 1] first row of each image
     self.batch = batch
     self.batch_index_offset = batch_index_offset
+
+
+# Explicit handle registry: id(cluster_indices tensor) -> (weak reference, SegmentMeta).  An
+# entry only answers for the very tensor object segment_by_kmeans returned (a copy, a slice or
+# a `.to()` of it is a different object and simply takes the general path); it disappears
+# with the tensor.
+_segment_registry = {}
+
+
+def _register_segments(tensor, meta):
+  key = id(tensor)
+  _segment_registry[key] = (weakref.ref(tensor, lambda _r, k=key: _segment_registry.pop(k, None)),
+                            meta)
+
+
+def segment_meta(tensor):
+  """SegmentMeta of a `cluster_indices` tensor returned by segment_by_kmeans, else None."""
+  entry = _segment_registry.get(id(tensor))
+  if entry is not None and entry[0]() is tensor:
+    return entry[1]
+  return None
 
 
 def calculate_prototypes_from_labels(embeddings, labels, max_label=None):
@@ -196,10 +217,65 @@ def segment_core(embeddings, labels, num_clusters, cluster_indices, local_featur
   return e, el, lab, inverse, bid, img_off, count, batch_index_offset
 
 
+def _prepare_seeds(embeddings, num_clusters, cluster_indices):
+  B, _, H, W = embeddings.shape
+  n = H * W
+  dev = embeddings.device
+  k_per_image = None
+  if cluster_indices is None:                                           # :320-323
+    seeds, num_k, dense = _seed_map(num_clusters, H, W, dev)
+    if not dense:
+      seeds, k_per_image, num_k = _compress_seed_maps(seeds.view(1, n).expand(B, n), B, n)
+      seeds = seeds.view(B, H, W)
+  else:
+    seeds, k_per_image, num_k = _compress_seed_maps(cluster_indices, B, n)
+    seeds = seeds.view(B, H, W)
+  return seeds, k_per_image, num_k
+
+
+def segment_clusters(embeddings, labels=None, num_clusters=[5, 5], cluster_indices=None,
+                     local_features=None, ignore_index=None, iterations=10,
+                     batch_index_offset=None, semantic_labels=None, instance_labels=None,
+                     label_divisor=None, semantic_ignore_index=None):
+  """segment_by_kmeans, optionally with the label packing of generate_clusters
+  (resnet_deeplab.py:112-117,134-135) done inside the library call: pass `semantic_labels`,
+  `instance_labels`, `label_divisor` and `semantic_ignore_index` instead of `labels`.  Returns
+  the 5-tuple of segment_by_kmeans, plus (semantic, instance) labels per kept pixel when a
+  divisor is given."""
+  if embeddings.dim() != 4:
+    raise ValueError('embeddings must be [batch, channels, height, width]')
+  if not embeddings.is_cuda:
+    raise RuntimeError('segment_by_kmeans: spml_b200 needs CUDA tensors (no CPU path)')
+  B, _, H, W = embeddings.shape
+  dev = embeddings.device
+  orig_dtype = embeddings.dtype
+  if orig_dtype in (torch.bfloat16, torch.float16):
+    # autocast backbones (BASELINE configs[2]): the head computes in fp32 like the reference
+    embeddings = embeddings.float()
+  if local_features is None:                                            # :313-317
+    local_features = _default_location(H, W, dev)
+  elif local_features.dtype != torch.float32:
+    local_features = local_features.float()
+  seeds, k_per_image, num_k = _prepare_seeds(embeddings, num_clusters, cluster_indices)
+  packed = semantic_labels is not None
+  if not packed and labels is None:                                     # :326-329
+    labels = torch.zeros((B, H, W), dtype=torch.long, device=dev)
+  if batch_index_offset is None:
+    batch_index_offset = B * (dev.index or 0)                           # :376-377
+  box = []
+  out = ops.SegmentByKmeansFn.apply(
+      embeddings, local_features, None if packed else labels, semantic_labels, instance_labels,
+      label_divisor, semantic_ignore_index, ignore_index, seeds, k_per_image, num_k, iterations,
+      batch_index_offset, box)
+  rows, segments, img_off = box[0]
+  _register_segments(out[3], SegmentMeta(segments, rows, img_off, B, batch_index_offset))
+  return out
+
+
 def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indices=None,
                       local_features=None, ignore_index=None, iterations=10,
                       batch_index_offset=None):
-  """spml/utils/segsort/common.py:270-408 as ~10 asynchronous launches and ONE host
+  """spml/utils/segsort/common.py:270-408 as ONE library call (~10 kernels) and ONE host
   synchronisation (to size the returned tensors).
 
   Returns (embeddings [N, C], embeddings_with_loc [N, C+L], labels [N],
@@ -207,11 +283,5 @@ def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indi
   `batch_index_offset` (extra keyword, default = the reference's
   `batch * device.index`) is the index given to the first image.
   """
-  e, el, lab, inverse, bid, img_off, count, offset = segment_core(
-      embeddings, labels, num_clusters, cluster_indices, local_features, ignore_index,
-      iterations, batch_index_offset)
-  B = embeddings.shape[0]
-  rows, segments = torch.stack([img_off[B], count[0]]).tolist()         # the one sync
-  cid = inverse[:rows]
-  cid._spml_meta = SegmentMeta(segments, rows, img_off, B, offset)
-  return e[:rows], el[:rows], lab[:rows], cid, bid[:rows]
+  return segment_clusters(embeddings, labels, num_clusters, cluster_indices, local_features,
+                          ignore_index, iterations, batch_index_offset)[:5]

@@ -20,11 +20,11 @@ def _check_mode(group_mode):
     raise NotImplementedError("spml_b200 implements group_mode='segsort+' only")
 
 
-def _loss(emb, pix_code, seg, protos, proto_code, kappa, mode, reduction):
+def _loss(emb, pix_code, seg, protos, proto_code, kappa, mode, reduction, path='auto'):
   if reduction not in _REDUCTIONS:
     raise NotImplementedError("spml_b200 implements reduction 'mean' and 'sum'")
   problem = ops.SegsortProblem(pix_code, seg, proto_code, kappa, mode,
-                               reduction=_REDUCTIONS[reduction])
+                               reduction=_REDUCTIONS[reduction], path=path)
   return ops.SegsortLossFn.apply(emb, protos, problem)
 
 
@@ -68,5 +68,7 @@ class SetSegSortLoss(_Loss):
               prototype_semantic_labels, prototype_weights=None):
     pix = ops.pack_tags(semantic_labels.view(-1, semantic_labels.shape[-1]))
     pro = ops.pack_tags(prototype_semantic_labels.view(-1, prototype_semantic_labels.shape[-1]))
+    # the tcgen05 epilogue compares 32-bit codes: wider tag sets take the fp32 kernels
+    path = 'fp32' if semantic_labels.shape[-1] > 32 else 'auto'
     return _loss(embeddings, pix, instance_labels, prototypes, pro, self.concentration,
-                 _lib.MODE_TAGS, self.reduction)
+                 _lib.MODE_TAGS, self.reduction, path=path)

@@ -40,16 +40,21 @@ def test_abi_version_and_error_text():
   assert b'unique_inverse' in lib.spml_last_error()
 
 
-def test_desc_layout_matches_c():
-  """sizeof(spml_segsort_desc) as the compiler sees it."""
-  src = '#include "spml_b200.h"\n#include <stdio.h>\nint main(){printf("%zu",sizeof(spml_segsort_desc));}'
-  exe = '/tmp/spml_desc_size'
+def test_struct_layouts_match_c():
+  """sizeof the three argument structs as a C compiler sees them == the ctypes mirrors ==
+  what the library reports (spml_sizeof_struct)."""
+  src = ('#include "spml_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu",'
+         'sizeof(spml_segsort_desc),sizeof(spml_cluster_args),sizeof(spml_head_args));}')
+  exe = '/tmp/spml_struct_sizes'
   r = subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe],
                      input=src, text=True, capture_output=True)
   assert r.returncode == 0, r.stderr
   import ctypes
-  assert int(subprocess.run([exe], capture_output=True, text=True).stdout) == ctypes.sizeof(
-      _lib.SegsortDesc)
+  sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+  lib = _lib.load()
+  for which, (size, struct) in enumerate(zip(sizes, (_lib.SegsortDesc, _lib.ClusterArgs,
+                                                     _lib.HeadArgs))):
+    assert size == ctypes.sizeof(struct) == lib.spml_sizeof_struct(which), struct.__name__
 
 
 def test_no_cpu_fallback():

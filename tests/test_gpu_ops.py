@@ -243,7 +243,7 @@ def test_gather_generic_path_equals_fast_path():
           [d['cluster_batch_index']], [d['cluster_semantic_label']],
           [d['cluster_instance_label']])
   fast = model_utils.gather_clustering_and_update_prototypes(*args)
-  plain = d['cluster_index'].clone()          # a copy carries no _spml_meta
+  plain = d['cluster_index'].clone()          # a copy is not in the segment registry
   args = (args[0], args[1], [plain]) + args[3:]
   slow = model_utils.gather_clustering_and_update_prototypes(*args)
   for a, c in zip(fast, slow):
@@ -265,3 +265,201 @@ def test_abi_rejects_bad_arguments():
     ops.nearest_prototype(x, x)
   with pytest.raises(RuntimeError, match='CUDA'):
     general_common.normalize_embedding(torch.zeros(3, 4))
+
+
+# ------------------------------------------------------------------------------ round 2
+
+
+@pytest.fixture(scope='module')
+def units2():
+  from conftest import load_golden
+  return load_golden('units2.pt')
+
+
+def test_nn_multiset_labels_golden(units2):
+  """models/utils.py:157-223 against the reference's outputs (k = 1, 3; separate queries)."""
+  for key in ('nn_tags_k1', 'nn_tags_k3'):
+    u = units2[key]
+    got = model_utils.gather_multiset_labels_per_batch_by_nearest_neighbor(
+        cu(u['p']), cu(u['p']), cu(u['psem']), cu(u['pbid']), cu(u['pbid']),
+        num_classes=u['num_classes'], top_k=u['top_k'], threshold=u['threshold'])
+    assert torch.equal(got.cpu(), u['tags']), key
+  u = units2['nn_tags_queries']
+  got = model_utils.gather_multiset_labels_per_batch_by_nearest_neighbor(
+      cu(u['q']), cu(u['p']), cu(u['psem']), cu(u['qbid']), cu(u['pbid']),
+      num_classes=u['num_classes'], top_k=u['top_k'], threshold=u['threshold'])
+  assert torch.equal(got.cpu(), u['tags'])
+
+
+def test_nn_multiset_labels_random():
+  g = torch.Generator().manual_seed(5)
+  m, d, nc = 700, 37, 15
+  base = O.l2_normalize(torch.randn(60, d, generator=g))
+  p = O.l2_normalize(base[torch.randint(0, 60, (m,), generator=g)] + 0.05 * torch.randn(m, d, generator=g))
+  pbid = torch.sort(torch.randint(0, 4, (m,), generator=g))[0]
+  psem = torch.randint(0, nc + 3, (m,), generator=g)
+  want = O.nn_multiset_labels(p, p, psem, pbid, pbid, nc, 1, 0.95)
+  got = model_utils.gather_multiset_labels_per_batch_by_nearest_neighbor(
+      cu(p), cu(p), cu(psem), cu(pbid), cu(pbid), num_classes=nc, top_k=1, threshold=0.95)
+  assert float((got.cpu() != want).float().mean()) < 1e-3     # similarities within 1 ulp of 0.95
+
+
+def test_predictions_golden(units2):
+  """Segsort.predictions (segsort.py:68-125): top-20 retrieval + majority vote."""
+  from spml_b200 import predictions
+  u = units2['predictions']
+  model = predictions.segsort(synth.make_config(synth.WORKLOADS['tiny']))
+  pred, topk = model.predictions(
+      {'cluster_embedding': cu(u['emb']), 'cluster_index': cu(u['cid'])},
+      {'semantic_memory_prototype': cu(u['bank']),
+       'semantic_memory_prototype_label': cu(u['bank_label'])})
+  assert torch.equal(topk.cpu(), u['topk'])
+  assert torch.equal(pred.cpu(), u['pred'])
+  out = model({'cluster_embedding': cu(u['emb']), 'cluster_index': cu(u['cid'])},
+              {'semantic_memory_prototype': cu(u['bank']),
+               'semantic_memory_prototype_label': cu(u['bank_label'])},
+              with_loss=False, with_prediction=True)
+  assert torch.equal(out['semantic_prediction'].cpu(), u['pred'])
+
+
+def test_segment_mean_one_hot_gather_datas(units2):
+  u = units2['segment_mean']
+  close(general_common.segment_mean(cu(u['x']), cu(u['index'])), u['mean'], 1e-6)
+  u = units2['one_hot']
+  assert torch.equal(general_common.one_hot(cu(u['labels'])).cpu(), u['auto'])
+  assert torch.equal(general_common.one_hot(cu(u['labels']), 8).cpu(), u['wide'])
+  u = units2['gather_datas']
+  got = model_utils.gather_and_update_datas([cu(t) for t in u['in']], 'cuda:0')
+  assert len(got) == 2
+  for a, b in zip(got, u['out']):
+    assert torch.equal(a.cpu(), b)
+
+
+def test_gather_two_device_lists_golden(units2):
+  """models/utils.py:41-131 over two-entry lists (the reference's multi-GPU semantics:
+  global batch indices, one prototype set for both) against the reference's outputs."""
+  u = units2['gather_two_devices']
+  L = {k: [cu(t) for t in v] for k, v in u['lists'].items()}
+  out = model_utils.gather_clustering_and_update_prototypes(
+      L['cluster_embedding'], L['cluster_embedding_with_loc'], L['cluster_index'],
+      L['cluster_batch_index'], L['cluster_semantic_label'], L['cluster_instance_label'], 'cuda:0')
+  for got, key in zip(out, ('prototype', 'prototype_with_loc', 'prototype_semantic_label',
+                            'prototype_instance_label', 'prototype_batch_index',
+                            'cluster_index')):
+    for a, b in zip(got, u['out'][key]):
+      if b.is_floating_point():
+        close(a.detach(), b)
+      else:
+        assert torch.equal(a.cpu(), b), key
+
+
+@pytest.mark.parametrize('n,dim,k', [(65536, 128, 256), (65536, 128, 1024), (262144, 128, 64)])
+def test_kmeans_sweep_sizes_match_oracle(n, dim, k):
+  """BASELINE configs[4] sizes (the regime the tcgen05 E-step is dispatched for): ids
+  bit-exact against the CPU oracle."""
+  prob = synth.sweep_problem(n, dim, k)
+  want = O.spherical_kmeans(prob['embedding'], prob['seed_label'], k, 10)
+  got = segsort_common.kmeans_with_initial_labels(cu(prob['embedding']), cu(prob['seed_label']),
+                                                  k, 10).cpu()
+  assert int((got != want).sum()) == 0
+
+
+def test_segsort_sweep_corner_matches_oracle():
+  """SegSort forward + backward at a sweep corner (N = 65 536, M = 1 024, D = 128) against the
+  fp64 oracle, row-chunked on the CPU side to bound memory."""
+  n, m, dim, kappa = 65536, 1024, 128, 10.0
+  g = torch.Generator().manual_seed(77)
+  protos = O.l2_normalize(torch.randn(m, dim, generator=g))
+  seg = torch.randint(0, m, (n,), generator=g)
+  psem = torch.randint(0, 21, (m,), generator=g)
+  e = O.l2_normalize(protos[seg] + 0.5 * torch.randn(n, dim, generator=g))
+  pr = protos.double().requires_grad_(True)
+  total = torch.zeros((), dtype=torch.float64)
+  de = torch.empty(n, dim, dtype=torch.float64)
+  for c0 in range(0, n, 8192):
+    ec = e[c0:c0 + 8192].double().requires_grad_(True)
+    part = O.segsort_loss(ec, psem[seg[c0:c0 + 8192]], seg[c0:c0 + 8192], pr, psem, kappa,
+                          reduction='sum') / n
+    part.backward()
+    total += part.detach()
+    de[c0:c0 + 8192] = ec.grad
+  ec, pc = cu(e).requires_grad_(True), cu(protos).requires_grad_(True)
+  got = segsort_loss.SegSortLoss(kappa)(ec, cu(psem[seg]), cu(seg), pc, cu(psem))
+  got.backward()
+  assert abs(float(got) - float(total)) <= 1e-4 * abs(float(total))
+  assert norm_err(ec.grad.cpu(), de) < 1e-3
+  assert norm_err(pc.grad.cpu(), pr.grad) < 1e-3
+
+
+def test_set_segsort_wide_tags_match_oracle():
+  """40 tag columns: bits 32..39 must take part (the tcgen05 epilogue compares 32-bit codes,
+  so wide tag sets run on the fp32 kernels)."""
+  g = torch.Generator().manual_seed(13)
+  n, m, dim, cols = 900, 150, 32, 40
+  protos = O.l2_normalize(torch.randn(m, dim, generator=g))
+  seg = torch.randint(0, m, (n,), generator=g)
+  ptags = torch.zeros(m, cols, dtype=torch.long)
+  ptags[torch.arange(m), torch.randint(32, cols, (m,), generator=g)] = 1   # only high bits
+  tags = ptags[seg]
+  e = O.l2_normalize(protos[seg] + 0.5 * torch.randn(n, dim, generator=g))
+  er, pr = e.double().requires_grad_(True), protos.double().requires_grad_(True)
+  want = O.set_segsort_loss(er, tags, seg, pr, ptags, 8.0)
+  want.backward()
+  ec, pc = cu(e).requires_grad_(True), cu(protos).requires_grad_(True)
+  got = segsort_loss.SetSegSortLoss(8.0)(ec, cu(tags), cu(seg), pc, cu(ptags))
+  got.backward()
+  assert abs(float(got) - float(want)) <= 2e-5 * abs(float(want))
+  assert norm_err(ec.grad.cpu(), er.grad) < 1e-4
+  assert norm_err(pc.grad.cpu(), pr.grad) < 1e-4
+
+
+def test_bf16_embeddings_are_accepted():
+  """BASELINE configs[2] feeds a bf16 (autocast) backbone output: the head computes in fp32
+  on the up-cast values and hands a bf16 gradient back."""
+  w = synth.WORKLOADS['small']
+  b = {k: v.cuda() for k, v in synth.make_batch(w).items()}
+  cfg = synth.make_config(w)
+  from spml_b200.head import ContrastiveHead
+  head = ContrastiveHead(cfg).cuda()
+  e16 = b['embedding'].bfloat16().requires_grad_(True)
+  out16 = head(e16, b['semantic_label'], b['instance_label'], b['semantic_tag'], b['local_feature'])
+  out16['loss'].backward()
+  e32 = e16.detach().float().requires_grad_(True)
+  out32 = head(e32, b['semantic_label'], b['instance_label'], b['semantic_tag'], b['local_feature'])
+  out32['loss'].backward()
+  assert e16.grad.dtype == torch.bfloat16
+  assert torch.equal(out16['datas']['cluster_index'], out32['datas']['cluster_index'])
+  assert abs(float(out16['loss']) - float(out32['loss'])) < 1e-6
+  assert norm_err(e16.grad.float().cpu(), e32.grad.cpu()) < 1e-2
+
+
+def test_inconsistent_labels_are_reported():
+  """The shortcut of gather_clustering_and_update_prototypes for ids fresh from
+  segment_by_kmeans checks on the device that the labels it is given are the ones the ids
+  were made from; a violation surfaces through the status word."""
+  w = synth.WORKLOADS['small']
+  b = {k: v.cuda() for k, v in synth.make_batch(w).items()}
+  from spml_b200.head import generate_clusters
+  d = generate_clusters(b['embedding'], b['semantic_label'], b['instance_label'],
+                        b['local_feature'], w.label_divisor, w.ignore_index,
+                        list(w.num_clusters), w.iterations)
+  ops.check_status()
+  wrong = torch.arange(d['cluster_index'].shape[0], device='cuda') % 7
+  model_utils.gather_clustering_and_update_prototypes(
+      [d['cluster_embedding']], [d['cluster_embedding_with_loc']], [d['cluster_index']],
+      [d['cluster_batch_index']], [wrong], [d['cluster_instance_label']])
+  with pytest.raises(RuntimeError, match='different semantic'):
+    ops.check_status()
+  ops.check_status()      # the word was cleared
+
+
+def test_calls_follow_the_tensor_device():
+  """every call runs on the device of its tensors, not on the thread's current
+  device (the reference's train.py gathers on cuda:{n-1} from a thread whose device is 0)."""
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs two GPUs')
+  x = torch.randn(64, 16, device='cuda:1')
+  with torch.cuda.device(0):
+    y = general_common.normalize_embedding(x)
+  assert y.device == x.device
+  close(y, O.l2_normalize(x.cpu()), 1e-6)

@@ -8,57 +8,79 @@ import pytest
 import torch
 
 from conftest import load_golden
-from helpers import check_step, cuda_step, norm_err, rel_err
+from helpers import check_step, cuda_step, make_head, norm_err, rel_err
 from oracle import spml_oracle as O
-from spml_b200 import synth
+from spml_b200 import ops, synth
 from spml_b200.head import ContrastiveHead
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('name', ['tiny', 'small'])
-def test_steps_match_reference_golden(name):
-  """Three consecutive steps (memory bank filling) against outputs of the reference."""
+@pytest.mark.parametrize('name,steps', [('tiny', 3), ('small', 3), ('tiny_softmax', 3),
+                                        ('tiny_densepose', 2), ('tiny_densepose_shipped', 1)])
+def test_steps_match_reference_golden(name, steps):
+  """Consecutive steps (memory bank filling) against outputs of the reference, for the three
+  heads: segsort.py, segsort_softmax.py (eval mode) and the DensePose variant."""
   w = synth.WORKLOADS[name]
   cfg = synth.make_config(w)
-  head = ContrastiveHead(cfg).cuda()
+  head = make_head(cfg, w)
+  cls64 = O.make_classifier(cfg, dtype=torch.float64).eval() if w.variant != 'segsort' else None
   bank64 = {}
-  for step in range(3):
+  escapes = []
+  for step in range(steps):
     g = load_golden('%s_step%d.pt' % (name, step))
-    ref64 = O.contrastive_step(cfg, g['inputs'], bank64, dtype=torch.float64)
+    ref64 = O.contrastive_step(cfg, g['inputs'], bank64, dtype=torch.float64, variant=w.variant,
+                               classifier=cls64)
     ours = cuda_step(head, g['inputs'])
-    msgs = check_step(ours, g['outputs'], ref64, what='%s step %d' % (name, step))
+    msgs = check_step(ours, g['outputs'], ref64, what='%s step %d' % (name, step),
+                      escapes=escapes)
     assert not msgs, '\n'.join(msgs)
     head.update_memory_bank()
     O.memory_bank_update(bank64, {k: ref64[k] for k in ref64 if k.startswith('prototype')},
                          w.memory_bank_size, w.batch)
-  assert len(head.memory_banks['memory_prototype']) == min(3, w.memory_bank_size)
+  assert not escapes, escapes       # nothing needed the fp64 criterion
+  if w.memory_bank_size:
+    assert len(head.memory_banks['memory_prototype']) == min(steps, w.memory_bank_size)
+  ops.check_status()
+
+
+# keys that may take check_step's fp64 criterion on a full-size workload, each with its reason;
+# anything else taking it fails the test
+ALLOWED_ESCAPES = ()
 
 
 @pytest.mark.parametrize('name,seed', [('voc_scribble_b1', 235), ('voc_scribble_b1', 236),
                                        ('voc_tag_b2', 235), ('densepose_b1', 235),
+                                       ('densepose_shape_voc_head_b1', 235),
+                                       ('voc_scribble_softmax_b1', 235),
                                        ('voc_scribble_b4', 235)])
 def test_workloads_match_oracle(name, seed):
   """BASELINE.json configs at full size: two steps (second one with a memory bank)."""
   w = synth.WORKLOADS[name]
-  if name == 'densepose_b1':
-    w = synth.dataclasses.replace(w, loc_channels=5)
   cfg = synth.make_config(w)
-  head = ContrastiveHead(cfg).cuda()
+  head = make_head(cfg, w)
+  cls = O.make_classifier(cfg).eval() if w.variant != 'segsort' else None
+  cls64 = O.make_classifier(cfg, dtype=torch.float64).eval() if w.variant != 'segsort' else None
   bank, bank64 = {}, {}
+  escapes = []
   torch.set_num_threads(max(1, torch.get_num_threads()))
   for step in range(2):
     batch = synth.make_batch(w, seed=seed, step=step)
-    ref = O.contrastive_step(cfg, batch, bank)
-    ref64 = O.contrastive_step(cfg, batch, bank64, dtype=torch.float64)
+    ref = O.contrastive_step(cfg, batch, bank, variant=w.variant, classifier=cls)
+    ref64 = O.contrastive_step(cfg, batch, bank64, dtype=torch.float64, variant=w.variant,
+                               classifier=cls64)
     ours = cuda_step(head, batch)
-    msgs = check_step(ours, ref, ref64, what='%s seed %d step %d' % (name, seed, step))
+    msgs = check_step(ours, ref, ref64, what='%s seed %d step %d' % (name, seed, step),
+                      escapes=escapes)
     assert not msgs, '\n'.join(msgs)
     head.update_memory_bank()
     O.memory_bank_update(bank, {k: ref[k] for k in ref if k.startswith('prototype')},
                          w.memory_bank_size, w.batch)
     O.memory_bank_update(bank64, {k: ref64[k] for k in ref64 if k.startswith('prototype')},
                          w.memory_bank_size, w.batch)
+  unexpected = [e for e in escapes if not any(a in e for a in ALLOWED_ESCAPES)]
+  assert not unexpected, unexpected
+  ops.check_status()
 
 
 def test_step_is_bit_reproducible():

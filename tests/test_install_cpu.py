@@ -27,9 +27,21 @@ def test_install_rebinds_and_uninstall_restores():
     pred = importlib.import_module('spml.models.predictions.segsort')
     assert pred.segsort_loss.SegSortLoss is spml_b200.segsort_loss.SegSortLoss
     assert pred.Segsort is spml_b200.predictions.Segsort
+    # A9: the generate_clusters METHOD of the embedding models, and the DensePose head
+    deeplab = importlib.import_module('spml.models.embeddings.resnet_deeplab')
+    psp_dp = importlib.import_module('spml.models.embeddings.resnet_pspnet_densepose')
+    dp = importlib.import_module('spml.models.predictions.segsort_softmax_densepose')
+    assert 'spml.models.embeddings.resnet_deeplab.ResnetDeeplab.generate_clusters' in done
+    assert deeplab.ResnetDeeplab.generate_clusters.__module__ == 'spml_b200.head'
+    assert psp_dp.ResnetPspnet.generate_clusters.__module__ == 'spml_b200.head'
+    assert dp.SegsortSoftmax is spml_b200.predictions.SegsortSoftmaxDensepose
+    mu = importlib.import_module('spml.models.utils')
+    assert (mu.gather_multiset_labels_per_batch_by_nearest_neighbor
+            is spml_b200.model_utils.gather_multiset_labels_per_batch_by_nearest_neighbor)
     spml_b200.uninstall()
     assert common.segment_by_kmeans is orig_fn and loss.SegSortLoss is orig_cls
-    assert len(inst.BINDINGS) == 7
+    assert deeplab.ResnetDeeplab.generate_clusters.__module__ == deeplab.__name__
+    assert len(inst.BINDINGS) == 11
   finally:
     sys.path.remove(REF)
     for k in [k for k in sys.modules if k == 'spml' or k.startswith('spml.')]:
