@@ -12,12 +12,17 @@ map, 6x6 seeds, 10 k-means iterations, memory bank of 2 steps.
 
 It prints ONE JSON line (see the keys below).  `value` is measured with the inputs
 resident in HBM; `e2e` with the inputs in pinned host memory, copied in, and the
-loss + d(embedding) copied back inside the timed region.  Multi-GPU: the path
+losses + accuracy copied back inside the timed region.  Multi-GPU: the path
 shards over images, every rank runs its own minibatch (weak scaling, no data-path
 collective; the head has no parameters so DDP would add none).
 
-`--impl reference` times the CPU oracle (a port of the reference with the same ATen
-ops; the Python reference itself cannot travel to the GPU box) on all host cores.
+`value` / `e2e` are measured through the reference's operator API (the symbols
+spml_b200.install() rebinds, composed as train.py does); the fixed-capacity CUDA-graph head
+is reported next to them under `static_head`.
+
+`--impl reference` times the reference's own CPU implementation on all host cores: the copy of
+twke18/SPML under baseline/_ref when it is there (scripts/install_reference.py), else the
+oracle port (same ATen CPU kernels in the same order).
 """
 
 from __future__ import annotations
@@ -47,11 +52,13 @@ FLUSH_BYTES = 256 << 20
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=30)
+  ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--workload', default='voc_scribble_b1', choices=sorted(synth.WORKLOADS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--repeats', type=int, default=0,
+                  help='timed regions of --steps steps each (0: enough for ~1.2 s of load)')
   ap.add_argument('--no-graph', action='store_true',
                   help='launch the kernels directly instead of replaying the CUDA graph (for ncu)')
   return ap.parse_args()
@@ -118,12 +125,60 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------ reference arm
 
 
+def reference_runner():
+  """(step function, kind): the reference's own CPU implementation of the path.  With the copy
+  of twke18/SPML under baseline/_ref (scripts/install_reference.py; it travels to the GPU box
+  with the snapshot) this IS the reference's code, driven as pyscripts/train/train.py:167-219
+  drives it (kind 'reference'); without it, the oracle port, which issues the same ATen CPU
+  kernels in the same order (kind 'port')."""
+  ref_root = os.path.join(ROOT, 'baseline', '_ref')
+  if os.path.isdir(os.path.join(ref_root, 'spml')):
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import reference_step
+    return reference_step.make_runner(ref_root), 'reference'
+  from oracle import spml_oracle as O
+
+  def step(cfg, w, batch, bank):
+    if w.variant != 'segsort' and w.name not in step.classifier:
+      step.classifier[w.name] = O.make_classifier(cfg).eval()
+    out = O.contrastive_step(cfg, batch, bank, variant=w.variant,
+                             classifier=step.classifier.get(w.name))
+    O.memory_bank_update(bank, {k: out[k] for k in out if k.startswith('prototype')},
+                         w.memory_bank_size, w.batch)
+    return out
+  step.classifier = {}
+  return step, 'port'
+
+
+def time_cpu_reference(w, cfg, warm, steps, budget_s):
+  """Times the reference's CPU path on a bounded sample of the workload, all host threads."""
+  step_fn, kind = reference_runner()
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  batches = [synth.make_batch(w, seed=235, step=s) for s in range(4)]
+  bank, times = {}, []
+  budget_end = time.perf_counter() + budget_s
+  for s in range(warm + steps):
+    t0 = time.perf_counter()
+    step_fn(cfg, w, batches[s % 4], bank)
+    if s >= warm:
+      times.append(time.perf_counter() - t0)
+    if time.perf_counter() > budget_end and len(times) >= 3:
+      break
+  return {'value': w.batch * len(times) / sum(times), 'unit': 'images/s', 'cores': cores,
+          'kind': kind,
+          'sample': '%d steps of %s after %d warm-ups, fp32 torch %s CPU ops, %d threads'
+                    % (len(times), w.name, warm, torch.__version__, cores),
+          'ms_per_step': 1e3 * sum(times) / len(times)}
+
+
 def run_reference(args):
-  """The reference's CPU implementation of the path (oracle port), all host threads."""
+  """The reference's CPU implementation of the path, all host threads.  Under torchrun rank 0
+  alone runs ONE CPU process on its own minibatch; the other ranks exit without work."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  from oracle import spml_oracle as O
+  step_fn, kind = reference_runner()
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   w = synth.WORKLOADS[args.workload]
@@ -134,15 +189,13 @@ def run_reference(args):
   for s in range(args.warmup + args.steps):
     batch = batches[s % len(batches)]
     t0 = time.perf_counter()
-    out = O.contrastive_step(cfg, batch, bank)
-    O.memory_bank_update(bank, {k: out[k] for k in out if k.startswith('prototype')},
-                         w.memory_bank_size, w.batch)
+    step_fn(cfg, w, batch, bank)
     dt = time.perf_counter() - t0
     if s >= args.warmup:
       times.append(dt)
   total = sum(times)
   value = w.batch * len(times) / total
-  sample = '%d steps of workload %s (batch %d), fp32, torch %s CPU ops' % (
+  sample = '%d steps of workload %s (batch %d), fp32, torch %s CPU ops, ONE process' % (
       len(times), w.name, w.batch, torch.__version__)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s',
@@ -150,7 +203,9 @@ def run_reference(args):
       'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': workload_config(w, args.gpus),
-      'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+      'note': 'one CPU process on rank 0 (batch %d) whatever --gpus says: the ratio against an '
+              'N-GPU run compares N GPUs with one CPU process' % w.batch,
+      'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': kind,
                        'sample': sample},
       'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
@@ -224,7 +279,7 @@ def roofline_of(key, sh, ms_per_call, launches_per_call, peaks):
 
 def run_b200(args):
   import torch.distributed as dist
-  from spml_b200 import _lib
+  from spml_b200 import _lib, ops
   from spml_b200.head import ContrastiveHead
   from spml_b200.static_head import StaticContrastiveHead
 
@@ -253,51 +308,68 @@ def run_b200(args):
 
   w = synth.WORKLOADS[args.workload]
   cfg = synth.make_config(w)
-  # the product path: fixed-capacity head, forward + backward + bank update as one CUDA graph
-  head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels, device=dev,
-                               use_graph=not args.no_graph)
-  dyn_head = ContrastiveHead(cfg).to(dev)     # reference-shaped drop-in API, timed for comparison
+  # THE PRODUCT PATH: the reference's operator API (generate_clusters ->
+  # gather_clustering_and_update_prototypes -> Segsort*.forward -> backward -> memory bank),
+  # data-dependent shapes, one host synchronisation per step
+  head = ContrastiveHead(cfg, variant=w.variant).to(dev)
+  # extra: the fixed-capacity CUDA-graph head (an API the reference does not have)
+  static_ok = w.variant == 'segsort' and w.sem_occ_loss_types == 'segsort'
+  static_head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels, device=dev,
+                                      use_graph=not args.no_graph) if static_ok else None
 
   # every rank gets its own minibatches (different seeds): weak scaling over images
   host = [synth.make_batch(w, seed=235 + rank, step=s) for s in range(POOL)]
   host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
   resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
   flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
-  h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+  keys = ('embedding', 'semantic_label', 'instance_label', 'semantic_tag', 'local_feature') + (
+      ('semantic_label_full',) if 'semantic_label_full' in host[0] else ())
+  h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in keys)
   grad_host = torch.empty(host[0]['embedding'].shape, dtype=torch.float32).pin_memory()
   loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
-  d2h_bytes = grad_host.numel() * 4 + loss_host.numel() * 4
 
   def args_of(b):
     return (b['embedding'], b['semantic_label'], b['instance_label'], b['semantic_tag'],
             b['local_feature'])
 
+  def run_head(b):
+    emb = b['embedding'].detach().requires_grad_(True)
+    out = head(emb, b['semantic_label'], b['instance_label'], b['semantic_tag'],
+               b['local_feature'], b.get('semantic_label_full'))
+    out['loss'].backward()
+    head.update_memory_bank(1)                         # train.py:276-293
+    return out, emb.grad
+
+  def losses_of(out):
+    zero = out['loss'].new_zeros(())
+    # detached: a copy_ of a tensor with a grad_fn into the pinned buffer would chain every
+    # step's autograd graph onto the buffer's history
+    return torch.stack([out[k].detach() if out.get(k) is not None else zero
+                        for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss', 'accuracy')])
+
   def step_resident(i):
-    return head.step(*args_of(resident[i % POOL]))
+    return run_head(resident[i % POOL])
 
   def step_e2e(i):
-    out = head.step(*args_of(host[i % POOL]))          # pinned host -> device inside the step
-    grad_host.copy_(out['grad_embedding'], non_blocking=True)
+    # pinned host -> device inside the step; back: what train.py reads every step (the three
+    # losses + accuracy, train.py:213-219); d(embedding) stays on the device for the backbone
+    hb = host[i % POOL]
+    out, _ = run_head({k: hb[k].to(dev, non_blocking=True) for k in keys})
+    loss_host.copy_(losses_of(out), non_blocking=True)
+
+  def step_e2e_grad(i):
+    hb = host[i % POOL]
+    out, grad = run_head({k: hb[k].to(dev, non_blocking=True) for k in keys})
+    grad_host.copy_(grad, non_blocking=True)
+    loss_host.copy_(losses_of(out), non_blocking=True)
+
+  def step_static(i):
+    return static_head.step(*args_of(resident[i % POOL]))
+
+  def step_static_e2e(i):
+    out = static_head.step(*args_of(host[i % POOL]))
     loss_host.copy_(torch.stack([out['sem_ann_loss'], out['sem_occ_loss'], out['img_sim_loss'],
                                  out['accuracy']]), non_blocking=True)
-    return out
-
-  def step_e2e_losses(i):
-    # the same with only what train.py reads back every step (losses + accuracy, train.py:213-219);
-    # in training d(embedding) stays on the device and feeds the backbone's backward
-    out = head.step(*args_of(host[i % POOL]))
-    loss_host.copy_(torch.stack([out['sem_ann_loss'], out['sem_occ_loss'], out['img_sim_loss'],
-                                 out['accuracy']]), non_blocking=True)
-    return out
-
-  def step_drop_in(i):
-    b = resident[i % POOL]
-    emb = b['embedding'].detach().requires_grad_(True)
-    out = dyn_head(emb, b['semantic_label'], b['instance_label'], b['semantic_tag'],
-                   b['local_feature'])
-    out['loss'].backward()
-    dyn_head.update_memory_bank(1)
-    return out
 
   def barrier():
     torch.cuda.synchronize()
@@ -305,18 +377,24 @@ def run_b200(args):
       dist.barrier()
       torch.cuda.synchronize()
 
-  def timed(step_fn, steps, warmup):
-    """Per-step CUDA-event timing on the launching stream with an L2 flush (untimed)
-    between steps; returns the summed milliseconds of `steps` steps."""
-    head.reset_memory_bank()
-    dyn_head.memory_banks.clear()
+  def reset_banks():
+    head.memory_banks.clear()
+    if static_head is not None:
+      static_head.reset_memory_bank()
+
+  def timed(step_fn, steps, warmup, repeats):
+    """`repeats` back-to-back regions of EXACTLY `steps` steps each, every step bracketed by
+    CUDA events on the launching stream with an (untimed) L2 flush in front of it; returns the
+    summed milliseconds of all steps * repeats steps, the library's kernel launches and the
+    wall time."""
+    reset_banks()
     for i in range(warmup):
       step_fn(i)
     barrier()
     pairs = []
     launches0 = _lib.launch_count()
     wall0 = time.perf_counter()
-    for i in range(steps):
+    for i in range(steps * repeats):
       flush.fill_(i & 0xff)
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
@@ -328,24 +406,10 @@ def run_b200(args):
     ms = sum(s.elapsed_time(e) for s, e in pairs)
     return ms, _lib.launch_count() - launches0, wall
 
-  sampler = ClockSampler(local_rank) if rank == 0 else None
-  if sampler:
-    sampler.start()
-    time.sleep(0.3)
-  step_resident(0)                       # builds the graph (untimed)
-  torch.cuda.synchronize()
-  kernels_per_step = head.kernels_per_step
-  if args.no_graph:
-    before = _lib.launch_count()
-    step_resident(1)
-    kernels_per_step = _lib.launch_count() - before
-  ms_res, _, wall_res = timed(step_resident, args.steps, max(args.warmup, 3))
-  ms_e2e, _, wall_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
-  ms_e2e_l, _, _ = timed(step_e2e_losses, args.steps, max(args.warmup, 3))
-  clocks = sampler.stop() if sampler else None
-  ms_dyn, _, _ = timed(step_drop_in, max(3, args.steps // 3), 3)
-  ms_dyn = ms_dyn / max(3, args.steps // 3)
-  launches = kernels_per_step * args.steps
+  warmup = max(args.warmup, 3)
+  # how many K-step regions make ~1.2 s of load (so that the clock sampler sees it)
+  probe_ms, _, _ = timed(step_resident, 5, warmup, 1)
+  repeats = args.repeats or int(min(200, max(1, round(1200.0 / max(probe_ms / 5 * args.steps, 1e-3)))))
 
   def max_over_ranks(x):
     if world == 1:
@@ -354,13 +418,36 @@ def run_b200(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
+  sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get('SPML_BENCH_NO_SAMPLER') else None
+  if sampler:
+    sampler.start()
+    time.sleep(0.3)
+  ms_res, launches, wall_res = timed(step_resident, args.steps, warmup, repeats)
+  ms_e2e, _, wall_e2e = timed(step_e2e, args.steps, warmup, repeats)
+  clocks = sampler.stop() if sampler else None
+  short = max(1, repeats // 4)
+  ms_e2e_g, _, _ = timed(step_e2e_grad, args.steps, warmup, short)
+  ops.check_status(dev)
+  static = None
+  if static_head is not None:
+    ms_s, launches_s, _ = timed(step_static, args.steps, warmup, short)
+    ms_se, _, _ = timed(step_static_e2e, args.steps, warmup, short)
+    static_head.check_overflow()         # a silent max_segments overflow would void the figure
+    ms_s, ms_se = max_over_ranks(ms_s), max_over_ranks(ms_se)
+    static = {'what': 'StaticContrastiveHead: fixed-capacity buffers, the whole step replayed as '
+                      'one CUDA graph, no host synchronisation (not a reference API)',
+              'ms_per_step': ms_s / (args.steps * short),
+              'e2e_ms_per_step': ms_se / (args.steps * short),
+              'kernels_per_step': static_head.kernels_per_step, 'cuda_graph': not args.no_graph}
+  n_timed = args.steps * repeats
   ms_res, ms_e2e = max_over_ranks(ms_res), max_over_ranks(ms_e2e)
-  ms_e2e_l = max_over_ranks(ms_e2e_l)
-  images = w.batch * world * args.steps
+  ms_e2e_g = max_over_ranks(ms_e2e_g)
+  images = w.batch * world * n_timed
 
-  # ---- per-entry-point profile of a few steps (separate pass; events per C-ABI call)
+  # ---- per-entry-point profile of a few steps (separate pass; events per C-ABI call of the
+  # fine-grained entry points, which launch the same kernels as the stage-group calls)
   roofline, breakdown = None, None
-  if rank == 0:
+  if rank == 0 and static_ok:
     prof_head = StaticContrastiveHead(cfg, w.batch, w.height, w.width, w.loc_channels,
                                       device=dev, use_graph=False)
     prof_head.collect_stats = True
@@ -368,7 +455,7 @@ def run_b200(args):
       prof_head.step(*args_of(resident[i % POOL]))
     torch.cuda.synchronize()
     _lib.PROFILE = []
-    prof_steps = 5
+    prof_steps = 10
     for i in range(prof_steps):
       flush.fill_(i)
       out = prof_head.step(*args_of(resident[(3 + i) % POOL]))
@@ -402,61 +489,47 @@ def run_b200(args):
     roofline = dict(per_kernel[top])
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (a profiler
     # number cannot be taken inside a timed run); null when this workload was not captured
-    tpath = os.path.join(ROOT, 'profiles', 'r1c_traffic.json')
-    if os.path.exists(tpath):
-      traffic = json.load(open(tpath))
-      roofline['traffic'] = traffic.get(w.name, {}).get(top)
-      roofline['traffic_source'] = traffic['source']
+    for tname in ('r2_traffic.json', 'r1c_traffic.json'):
+      tpath = os.path.join(ROOT, 'profiles', tname)
+      if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+        roofline['traffic'] = traffic.get(w.name, {}).get(top)
+        roofline['traffic_source'] = traffic['source']
+        break
     roofline['shapes'] = shapes
     roofline['all'] = {k: {'bound': v['bound'], 'frac': v['frac'], 'ms_per_call': v['ms_per_call'],
                            'roofline_ms_per_call': v['roofline_ms_per_call']}
                        for k, v in per_kernel.items()}
 
-  # ---- CPU baseline (oracle port) on this box's host cores, rank 0, N == 1 only
+  # ---- CPU baseline on this box's host cores, rank 0, N == 1 only
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    from oracle import spml_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cpu_batches = [synth.make_batch(w, seed=235, step=s) for s in range(4)]
-    bank, times = {}, []
-    budget_end = time.perf_counter() + 20.0
-    for s in range(2 + 12):
-      t0 = time.perf_counter()
-      o = O.contrastive_step(cfg, cpu_batches[s % 4], bank)
-      O.memory_bank_update(bank, {k: o[k] for k in o if k.startswith('prototype')},
-                           w.memory_bank_size, w.batch)
-      if s >= 2:
-        times.append(time.perf_counter() - t0)
-      if time.perf_counter() > budget_end and len(times) >= 3:
-        break
-    cpu_baseline = {'value': w.batch * len(times) / sum(times), 'unit': 'images/s',
-                    'cores': cores, 'kind': 'port',
-                    'sample': '%d steps of %s after 2 warm-ups, fp32 torch CPU ops, %d threads'
-                              % (len(times), w.name, cores),
-                    'ms_per_step': 1e3 * sum(times) / len(times)}
+    cpu_baseline = time_cpu_reference(w, cfg, warm=2, steps=12, budget_s=20.0)
 
   if rank == 0:
     value = images / (ms_res * 1e-3)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': args.steps, 'warmup': warmup, 'repeats': repeats, 'timed_steps': n_timed,
+        'ms_per_step': ms_res / n_timed, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(w, world),
-        'contrastive_step_ms': ms_res / args.steps,
+        'api': 'the reference operator API (spml_b200.install symbols composed as train.py:167-293 '
+               'does): data-dependent shapes, one host synchronisation per step',
+        'contrastive_step_ms': ms_res / n_timed,
         'e2e': {'value': images / (ms_e2e * 1e-3), 'unit': 'images/s',
-                'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': d2h_bytes,
-                'd2h': 'three losses, accuracy and d(loss)/d(embedding)',
-                # secondary: what a training loop moves (the gradient stays on the device)
-                'losses_only': {'value': images / (ms_e2e_l * 1e-3),
-                                'ms_per_step': ms_e2e_l / args.steps,
-                                'd2h_bytes_per_step': loss_host.numel() * 4}},
+                'ms_per_step': ms_e2e / n_timed, 'h2d_bytes_per_step': h2d_bytes,
+                'd2h_bytes_per_step': loss_host.numel() * 4,
+                'd2h': 'three losses + accuracy (what train.py:213-219 reads); d(embedding) '
+                       'stays on the device for the backbone',
+                # secondary: the gradient copied out as well
+                'with_gradient_copy': {
+                    'value': w.batch * world * args.steps * short / (ms_e2e_g * 1e-3),
+                    'ms_per_step': ms_e2e_g / (args.steps * short),
+                    'd2h_bytes_per_step': grad_host.numel() * 4 + loss_host.numel() * 4}},
         'gpu_launches': launches,
-        'gpu_launches_per_step': kernels_per_step,
-        'cuda_graph': not args.no_graph,
-        'drop_in_api_ms_per_step': ms_dyn,
+        'gpu_launches_per_step': launches / n_timed,
+        'static_head': static,
         'wall_s': {'resident': round(wall_res, 4), 'e2e': round(wall_e2e, 4)},
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'breakdown': breakdown,

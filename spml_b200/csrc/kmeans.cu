@@ -315,20 +315,26 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
       256);
 }
 
-// Which E-step runs (both return the same labels, bit for bit).  Measured on B200
-// (profiles/r1c_*): the tcgen05 kernel wins when each CTA keeps its one tile resident (batch
-// 1 at 128 x 128: 0.175 vs 0.19 ms) and when the assignment GEMM is big (K >= 256: 1.2-2.8x).
-// With several tiles per SM and a small K it ties with the fp32 kernel as long as its second
-// fp32 tile buffer (cp.async prefetch) fits, i.e. up to ~96 channels (the shipped batch 4:
-// 0.455 vs 0.463 ms); without it (D = 128, K = 64: 1.0 vs 0.6 ms) the fp32 kernel's 2-4
-// co-resident CTAs per SM hide the per-tile latencies better and keep that corner.
-// SPML_B200_KMEANS=fp32|tc overrides (read per call so that tests can compare the two).
-static bool kmeans_use_tc(int dim, int num_clusters, int64_t tiles, int sms) {
-  if (!spml::kmeans_tc_supported(dim)) return false;
+// Which kernel runs (all three return the same labels, bit for bit).
+//  * K <= 128 (every shipped configuration): kmeans_small.cu, the tcgen05 E-step with the
+//    prototypes rebuilt from the sums inside every CTA (no finalising CTA / flag / TMA chain).
+//  * otherwise, measured on B200 (profiles/r1c_*): the tcgen05 kernel of kmeans_tc.cu wins when
+//    the assignment GEMM is big (K >= 256: 1.2-2.8x) and whenever its second fp32 tile buffer
+//    (cp.async prefetch) fits, i.e. up to ~96 channels; the corner "many tiles per SM, D > 96"
+//    stays on the fp32 kernel, whose 2-4 co-resident CTAs per SM hide the per-tile latencies.
+// SPML_B200_KMEANS=fp32|tc|small overrides (read per call so that tests can compare them).
+enum KmeansPath { kPathFp32, kPathTc, kPathSmall };
+
+static KmeansPath kmeans_path(int dim, int num_clusters, int64_t tiles, int sms) {
+  const bool small_ok = spml::kmeans_small_supported(dim, num_clusters);
+  const bool tc_ok = spml::kmeans_tc_supported(dim);
   const char* e = getenv("SPML_B200_KMEANS");
-  if (e && !strcmp(e, "fp32")) return false;
-  if (e && !strcmp(e, "tc")) return true;
-  return tiles <= sms || num_clusters >= 256 || dim <= 96;
+  if (e && !strcmp(e, "fp32")) return kPathFp32;
+  if (e && !strcmp(e, "tc") && tc_ok) return kPathTc;
+  if (e && !strcmp(e, "small") && small_ok) return kPathSmall;
+  if (small_ok) return kPathSmall;
+  if (!tc_ok) return kPathFp32;
+  return (tiles <= sms || num_clusters >= 256 || dim <= 96) ? kPathTc : kPathFp32;
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {
@@ -365,9 +371,10 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   int device = 0, sms = 0, per_sm = 0;
   SPML_CUDA(cudaGetDevice(&device));
   SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const bool use_tc =
-      kmeans_use_tc(dim, num_clusters, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
-  const int replicas = use_tc ? kKmReplicas : 1;
+  const KmeansPath path =
+      kmeans_path(dim, num_clusters, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
+  const bool use_tc = path == kPathTc;
+  const int replicas = path == kPathFp32 ? 1 : kKmReplicas;
   const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, replicas);
   SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
 
@@ -394,6 +401,7 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.labels_out64 = labels_out_i64;
   p.eps = 1e-12f;
 
+  if (path == kPathSmall) return kmeans_small_launch(p, sms, st);
   if (use_tc)
     return kmeans_tc_launch(p, base + kmeans_split_offset(batch, num_clusters, dim, iterations),
                             sms, st);

@@ -65,6 +65,10 @@ __device__ __forceinline__ void split_fixed(float v, int& hi, int& lo) {
 constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
 constexpr int kKmReplicas = 2;   // copies of the segment sums in the tensor-core path
 
+// kmeans_small.cu (K <= 128: prototypes rebuilt from the sums inside every CTA)
+bool kmeans_small_supported(int dim, int num_clusters);
+int kmeans_small_launch(const KmeansArgs& p, int sms, cudaStream_t st);
+
 // kmeans_tc.cu
 bool kmeans_tc_supported(int dim);
 size_t kmeans_tc_split_bytes(int batch, int num_clusters, int dim, int iterations);

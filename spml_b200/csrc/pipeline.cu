@@ -73,12 +73,16 @@ static int join_stream(StreamPool& p, int i, cudaStream_t waiter) {
     if (rc__ != SPML_OK) return rc__; \
   } while (0)
 
+// Carves 256-byte aligned regions out of a workspace.  With a null base (size queries) the
+// regions still get distinct NON-NULL addresses that are never dereferenced: the plans test
+// pointers for null-ness (proto_valid, row_index, ...) and must size themselves identically
+// in both modes.
 struct Carver {
   char* base;
   size_t off;
   template <typename T>
   T* take(size_t count) {
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    T* p = reinterpret_cast<T*>((base ? base : reinterpret_cast<char*>(size_t(1) << 20)) + off);
     off += align_up(std::max<size_t>(count, 1) * sizeof(T), 256);
     return p;
   }

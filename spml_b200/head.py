@@ -116,16 +116,20 @@ class ContrastiveHead(nn.Module):
 
   @torch.no_grad()
   def update_memory_bank(self, num_replicas=1):
-    """train.py:276-293: FIFO of detached 'prototype*' entries; stored batch indices
-    move up by batch_size * num_gpus every step."""
+    """train.py:276-293: FIFO of detached 'prototype*' entries; stored batch indices move up
+    by batch_size * num_gpus every step.  The reference clones every entry; the tensors
+    here are this step's own outputs, which nothing writes to afterwards, so the bank keeps
+    them as they are (detached) and the batch indices are re-created, not updated in place."""
     if self._last_targets is None:
       return
     for k, v in self._last_targets.items():
       if 'prototype' in k and 'memory' not in k and torch.is_tensor(v):
         bank = self.memory_banks.setdefault('memory_' + k, [])
-        bank.append(v.clone().detach())
+        bank.append(v.detach())
         if len(bank) > self.memory_bank_size:
           self.memory_banks['memory_' + k] = bank[1:]
-    for t in self.memory_banks.get('memory_prototype_batch_index', []):
-      t += self._last_batch * num_replicas
+    key = 'memory_prototype_batch_index'
+    if key in self.memory_banks:
+      stride = self._last_batch * num_replicas
+      self.memory_banks[key] = [t + stride for t in self.memory_banks[key]]
     self._last_targets = None

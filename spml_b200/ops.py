@@ -523,6 +523,7 @@ class SegmentByKmeansFn(torch.autograd.Function):
     ctx.save_for_backward(e, el, nx, nc, dst)
     ctx.dims = (B, D, loc_ch, H, W)
     ctx.mark_non_differentiable(*outs[2:])
+    ctx.set_materialize_grads(False)
     box.append((rows, segments, ibuf[:B + 1]))
     return tuple(outs)
 
@@ -530,6 +531,8 @@ class SegmentByKmeansFn(torch.autograd.Function):
   def backward(ctx, de, del_, *_):
     e, el, nx, nc, dst = ctx.saved_tensors
     B, D, loc_ch, H, W = ctx.dims
+    if de is None and del_ is None:
+      return (None,) * 14
     demb = torch.empty(B, D, H, W, dtype=torch.float32, device=e.device)
     de = _f32c(de, 'd(cluster_embedding)') if de is not None else None
     del_ = _f32c(del_, 'd(cluster_embedding_with_loc)') if del_ is not None else None
@@ -566,6 +569,7 @@ class GatherPrototypesFn(torch.autograd.Function):
     ctx.save_for_backward(protos, protos_loc, norms, norms_loc, cid)
     p_sem, p_inst, p_bid = plab[0], plab[1], plab[2]
     ctx.mark_non_differentiable(p_sem, p_inst, p_bid)
+    ctx.set_materialize_grads(False)       # an unused prototype set costs nothing in the backward
     return protos, protos_loc, p_sem, p_inst, p_bid
 
   @staticmethod

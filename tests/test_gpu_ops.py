@@ -82,6 +82,8 @@ def test_kmeans_matches_oracle(n, dim, k):
 
 
 @pytest.mark.parametrize('n,dim,k,batch', [(5000, 66, 36, 1), (20000, 66, 36, 3), (3000, 37, 300, 1),
+                                           (60000, 66, 36, 4), (37636, 37, 128, 1), (70000, 130, 64, 2),
+                                           (16000, 66, 64, 2), (700, 5, 7, 3),
                                            (9000, 128, 1000, 1), (4097, 64, 129, 2),
                                            (130, 16, 7, 1),
                                            # several tiles per CTA AND several prototype tiles per
@@ -99,11 +101,13 @@ def test_kmeans_tensor_core_equals_fp32(n, dim, k, batch, monkeypatch):
     per = (n + batch - 1) // batch
     img_off = torch.tensor([min(i * per, n) for i in range(batch + 1)], dtype=torch.int32).cuda()
     got = {}
-    for path in ('fp32', 'tc'):
+    paths = ('fp32', 'tc') + (('small',) if k <= 128 else ())   # 'small': kmeans_small.cu
+    for path in paths:
       monkeypatch.setenv('SPML_B200_KMEANS', path)
       got[path], _ = ops.kmeans(e, img_off, batch, per, k, 10, lab0, want_i64=False)
       torch.cuda.synchronize()
-    assert torch.equal(got['fp32'], got['tc']), int((got['fp32'] != got['tc']).sum())
+    for path in paths[1:]:
+      assert torch.equal(got['fp32'], got[path]), (path, int((got['fp32'] != got[path]).sum()))
 
 
 def test_prepare_prototype_labels(units):
