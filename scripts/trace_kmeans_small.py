@@ -1,0 +1,29 @@
+"""Timeline of kmeans_small_kernel (cycles, CTA 0, its last tile of each pass).  Needs a trace
+build next to the product library:
+    make -C spml_b200/csrc BUILD=build_trace TARGET=../libspml_b200_trace.so EXTRA=-DSPML_KM_TRACE
+    SPML_B200_LIB=spml_b200/libspml_b200_trace.so python scripts/trace_kmeans_small.py [workload]"""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spml_b200 import _lib, synth
+from spml_b200.head import generate_clusters
+name = sys.argv[1] if len(sys.argv) > 1 else 'voc_scribble_b1'
+w = synth.WORKLOADS[name]
+for s in range(3):
+  b = {k: v.cuda() for k, v in synth.make_batch(w, step=s).items()}
+  generate_clusters(b['embedding'], b['semantic_label'], b['instance_label'], b['local_feature'],
+                    w.label_divisor, w.ignore_index, list(w.num_clusters), w.iterations)
+torch.cuda.synchronize()
+lib = _lib.load()
+tr = (ctypes.c_longlong * 256)()
+lib.spml_debug_kms_trace.argtypes = [ctypes.c_void_p]
+assert lib.spml_debug_kms_trace(tr) == 0
+t = torch.tensor(list(tr)).view(16, 16)
+names = {1: 'tile ready', 2: 'done seen', 11: 'staged', 12: 'carried', 13: 'normalised', 3: 'protos built', 4: 'mma done', 5: 'merged',
+         6: 'rechecked', 10: 'sorted', 7: 'accumulated', 8: 'flushed', 9: 'counted'}
+print(name, '(cycles since the CTA that owns tile 0 started its last tile of the pass)')
+for it in range(w.iterations + 1):
+  r = t[it]
+  ev = ' '.join('%s@%d' % (names[k], int(r[k] - r[0])) for k in (1, 2, 11, 12, 13, 3, 4, 5, 6, 10, 7, 8, 9) if r[k] != 0)
+  nxt = int(t[it + 1][0] - r[0]) if it < w.iterations else 0
+  print('it %2d  %s   next pass @%d' % (it, ev, nxt))

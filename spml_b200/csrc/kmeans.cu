@@ -325,8 +325,8 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
 // SPML_B200_KMEANS=fp32|tc|small overrides (read per call so that tests can compare them).
 enum KmeansPath { kPathFp32, kPathTc, kPathSmall };
 
-static KmeansPath kmeans_path(int dim, int num_clusters, int64_t tiles, int sms) {
-  const bool small_ok = spml::kmeans_small_supported(dim, num_clusters);
+static KmeansPath kmeans_path(int dim, int num_clusters, int batch, int64_t tiles, int sms) {
+  const bool small_ok = spml::kmeans_small_supported(dim, num_clusters, batch, tiles * spml::BM);
   const bool tc_ok = spml::kmeans_tc_supported(dim);
   const char* e = getenv("SPML_B200_KMEANS");
   if (e && !strcmp(e, "fp32")) return kPathFp32;
@@ -372,9 +372,9 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   SPML_CUDA(cudaGetDevice(&device));
   SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const KmeansPath path =
-      kmeans_path(dim, num_clusters, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
+      kmeans_path(dim, num_clusters, batch, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
   const bool use_tc = path == kPathTc;
-  const int replicas = path == kPathFp32 ? 1 : kKmReplicas;
+  const int replicas = path == kPathTc ? kKmReplicas : 1;   // the small-K kernel pre-reduces per CTA
   const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, replicas);
   SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
 

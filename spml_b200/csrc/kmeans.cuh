@@ -66,7 +66,7 @@ constexpr int kAccSlots = (SPML_MAX_DIM + 31) / 32;
 constexpr int kKmReplicas = 2;   // copies of the segment sums in the tensor-core path
 
 // kmeans_small.cu (K <= 128: prototypes rebuilt from the sums inside every CTA)
-bool kmeans_small_supported(int dim, int num_clusters);
+bool kmeans_small_supported(int dim, int num_clusters, int batch, int64_t rows);
 int kmeans_small_launch(const KmeansArgs& p, int sms, cudaStream_t st);
 
 // kmeans_tc.cu

@@ -10,10 +10,13 @@
 //     counter is complete (one batch of L2 loads, all in flight together), normalises them
 //     and writes the bf16 hi / lo operand tile and the fp32 rows straight into its own shared
 //     memory: no finalising CTA, no flag, no TMA, no prototype traffic through global memory;
-//   * the M-step accumulates a tile with native 32-bit shared-memory atomics on the two
-//     halves of the exact fixed-point value (hi * 2^16 + lo = round(x 2^32)), then adds only
-//     the non-zero entries to the global sums with 64-bit reductions: no ranking pass, and
-//     several consecutive tiles of a CTA share one flush.
+//   * the M-step is INCREMENTAL: pass 0 sums every row once; afterwards only the rows whose
+//     label changed move (- x from the old cluster, + x to the new one; 39 % of the rows in
+//     pass 1 of the VOC workload, under 1 % from pass 6 on) and the image's previous totals
+//     are carried over by the CTAs in equal slices.  Sums are exact fixed-point integers, so
+//     this is the same arithmetic as re-summing everything.  A tile's contribution is gathered
+//     with native 32-bit shared-memory atomics on the two halves of round(x 2^32) and only its
+//     non-zero entries go to the global sums (64-bit reductions).
 // Sums are integers, so labels are bit-identical to the fp32 kernel and to kmeans_tc.cu
 // whatever the tiling (tests/test_gpu_ops.py::test_kmeans_tensor_core_equals_fp32).
 #include <math.h>
@@ -28,13 +31,14 @@ namespace spml {
 constexpr int kSmBN = 128;                 // prototype rows of the operand tile
 constexpr int kSmBlockBytes = 128 * 128;   // one 64-wide K block of a 128-row bf16 tile
 constexpr int kSmWarps = kGemmThreads / 32;
+constexpr int kSmMaxBatch = 255;           // images per call (offsets cached in shared memory)
 constexpr int kSmMaxTilesPerFlush = 24;    // 2^19 * 128 * 24 < 2^31: the hi halves cannot overflow
 
 #ifdef SPML_KM_TRACE
 __device__ long long g_kms_trace[16 * 16];
 #define KMS(slot)                                                                          \
   do {                                                                                     \
-    if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) g_kms_trace[it * 16 + (slot)] = clock64(); \
+    if (lt0 == 0 && lt1 > 0 && threadIdx.x == 0 && it < 16) g_kms_trace[it * 16 + (slot)] = clock64(); \
   } while (0)
 #else
 #define KMS(slot) do { } while (0)
@@ -73,17 +77,20 @@ __device__ __forceinline__ uint32_t operand_offset(int row, int d) {
          (((((uint32_t)d & 63) >> 3) ^ sw) << 4) + ((uint32_t)d & 7) * 2;
 }
 
-// live tile `lt` (image-major order) -> image, first row, row count
-__device__ __forceinline__ void kms_locate_tile(const KmeansArgs& p, int lt, Tile& tile) {
+// live tile `lt` (image-major order) -> image, first row, row count; also the image's first
+// live tile index and its number of tiles.  `off` = the image offsets (shared-memory copy).
+__device__ __forceinline__ void kms_locate_tile(const int* off, int lt, Tile& tile,
+                                                int* img_base = nullptr, int* img_tiles = nullptr) {
   int img = 0, base = 0;
   for (;;) {
-    const int64_t first = p.img_off ? (int64_t)p.img_off[img] : 0;
-    const int64_t last = p.img_off ? (int64_t)p.img_off[img + 1] : p.rows_total;
-    const int tiles_b = (int)((last - first + BM - 1) / BM);
+    const int first = off[img], last = off[img + 1];
+    const int tiles_b = (last - first + BM - 1) >> 7;
     if (lt < base + tiles_b) {
       tile.b = img;
       tile.row0 = first + (int64_t)(lt - base) * BM;
-      tile.rows = (int)min((int64_t)BM, last - tile.row0);
+      tile.rows = min(BM, last - (int)tile.row0);
+      if (img_base) *img_base = base;
+      if (img_tiles) *img_tiles = tiles_b;
       return;
     }
     base += tiles_b;
@@ -109,42 +116,30 @@ __device__ __forceinline__ int kms_prefetch_tile(const KmeansArgs& p, const Tile
   return lead;
 }
 
-// The image's unit prototypes from its fixed-point sums (common.py:39: sum / max(||sum||, eps);
-// an empty cluster is the zero vector), written to THIS CTA's shared memory: fp32 rows for the
-// exact re-check and the bf16 hi / lo operand tile.  One warp per prototype, lanes across the
-// channels, the loads of kC prototypes x R replicas in flight together.
-template <int kSlots, int R>
+// The image's unit prototypes from its fixed-point totals (common.py:39: sum / max(||sum||,
+// eps); an empty cluster is the zero vector), staged in shared memory, written to THIS CTA's
+// shared memory: fp32 rows for the exact re-check and the bf16 hi / lo operand tile.  One warp
+// per prototype, lanes across the channels.
+template <int kSlots>
 __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
-                                                 const long long* __restrict__ sums_it,
-                                                 size_t per_iter, int kb, float* __restrict__ pf,
+                                                 const long long* __restrict__ totals, int kb,
+                                                 float* __restrict__ pf,
                                                  uint8_t* __restrict__ b_tile) {
+  // kC prototypes per warp and round, interleaved: the chains (shuffle reduction, sqrt, IEEE
+  // divisions) of one prototype are ~900 cycles long with two warps per scheduler
   constexpr int kC = 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dim = p.dim;
   for (int kbase = warp; kbase < kb; kbase += kC * kSmWarps) {
-    long long raw[kC][kSlots][R];
-#pragma unroll
-    for (int i = 0; i < kC; ++i) {
-      const int k = kbase + i * kSmWarps;
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        const int d = lane + 32 * s;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          raw[i][s][r] = (k < kb && d < dim)
-                             ? __ldcg(sums_it + (size_t)r * per_iter + (size_t)k * dim + d) : 0;
-      }
-    }
     float v[kC][kSlots], ss[kC];
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
+      const int k = kbase + i * kSmWarps;
       ss[i] = 0.f;
 #pragma unroll
       for (int s = 0; s < kSlots; ++s) {
-        long long t = raw[i][s][0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) t += raw[i][s][r];
-        v[i][s] = fixed_to_float(t);
+        const int d = lane + 32 * s;
+        v[i][s] = (k < kb && d < dim) ? fixed_to_float(totals[k * dim + d]) : 0.f;
         ss[i] += v[i][s] * v[i][s];
       }
     }
@@ -176,40 +171,109 @@ __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
   }
 }
 
-// M-step of one tile into the CTA's shared sums: the two exact halves of round(x 2^32) with
-// native 32-bit shared atomics (a 64-bit shared atomicAdd compiles to a CAS loop).  Warp w
-// takes rows 16 w .. 16 w + 15, lanes across the channels.
-template <int kSlots>
-__device__ __forceinline__ bool accumulate_tile(int rows, int dim, int num_clusters,
-                                                const float* __restrict__ xs,
-                                                const int* __restrict__ s_lab, int* s_hi,
-                                                int* s_lo) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kPer = BM / kSmWarps;
+// s_order[i] = i-th row of the tile in label order (counting sort over K <= 128 labels; the
+// order inside a label is whatever the atomics give: the sums are integers, so it is free).
+// Rows with a label outside [0, K) are left out (reported through the return value).
+__device__ __forceinline__ bool sort_rows_by_label(const int* s_lab, int rows, int num_clusters,
+                                                   int* s_cnt, unsigned char* s_order,
+                                                   int* s_sorted) {
+  const int tid = threadIdx.x;
+  if (tid < kSmBN) s_cnt[tid] = 0;
+  __syncthreads();
+  int lab = -1, pos = 0;
   bool bad = false;
-#pragma unroll 4
-  for (int i = 0; i < kPer; ++i) {
-    const int r = warp * kPer + i;
-    if (r >= rows) break;
-    const int lab = s_lab[r];
-    if ((unsigned)lab >= (unsigned)num_clusters) {   // a label the caller never declared
-      bad = true;
-      continue;
+  if (tid < rows) {
+    lab = s_lab[tid];
+    if ((unsigned)lab < (unsigned)num_clusters) pos = atomicAdd(&s_cnt[lab], 1);
+    else lab = -1, bad = true;
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive prefix over the 128 counters: four per lane + a warp scan
+    int c[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = s_cnt[tid * 4 + j], sum += c[j];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
     }
-    const int base = lab * dim;
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_cnt[tid * 4 + j] = run, run += c[j];
+    if (tid == 31) *s_sorted = incl;   // rows that take part
+  }
+  __syncthreads();
+  if (lab >= 0) s_order[s_cnt[lab] + pos] = (unsigned char)tid;
+  __syncthreads();
+  return bad;
+}
+
+// M-step of one tile into the CTA's shared sums.  Warp w takes 16 consecutive entries of the
+// label order, lanes across the channels, sums a run of equal labels in registers as the two
+// exact halves of round(x 2^32) (hi * 2^16 + lo; at most 16 rows per run, neither half can
+// overflow) and adds a run to the shared sums with native 32-bit atomics when the label
+// changes: about (labels in the tile + 8) flushes per tile.
+template <int kSlots>
+__device__ __forceinline__ bool accumulate_tile(int sorted, int dim, const float* __restrict__ xs,
+                                                const int* __restrict__ s_lab,
+                                                const unsigned char* __restrict__ s_order,
+                                                int* s_hi, int* s_lo) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kPer = BM / kSmWarps;   // 16
+  const int e0 = warp * kPer;
+  int run_hi[kSlots], run_lo[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) run_hi[s] = run_lo[s] = 0;
+  int run_lab = -1;
+  bool bad = false;
+  auto flush = [&]() {
+    if (run_lab < 0) return;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
       const int d = lane + 32 * s;
       if (d < dim) {
-        const float v = xs[r * dim + d];
-        bad |= !(fabsf(v) <= 8.f);
+        atomicAdd(&s_hi[run_lab * dim + d], run_hi[s]);
+        atomicAdd(&s_lo[run_lab * dim + d], run_lo[s]);
+      }
+      run_hi[s] = run_lo[s] = 0;
+    }
+  };
+#pragma unroll
+  for (int g = 0; g < kPer / 4; ++g) {
+    // four rows in flight: all their shared-memory loads are issued before the first add
+    float v[4][kSlots];
+    int lab4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + g * 4 + u;
+      const bool ok = e < sorted;
+      const int row = ok ? s_order[e] : 0;
+      lab4[u] = ok ? s_lab[row] : -1;
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s) {
+        const int d = lane + 32 * s;
+        v[u][s] = (ok && d < dim) ? xs[row * dim + d] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (lab4[u] < 0) continue;        // past the end of the tile (warp-uniform)
+      if (lab4[u] != run_lab) {
+        flush();
+        run_lab = lab4[u];
+      }
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s) {
+        bad |= !(fabsf(v[u][s]) <= 8.f);
         int hi, lo;
-        split_fixed(v, hi, lo);
-        atomicAdd(&s_hi[base + d], hi);
-        atomicAdd(&s_lo[base + d], lo);
+        split_fixed(v[u][s], hi, lo);
+        run_hi[s] += hi;
+        run_lo[s] += lo;
       }
     }
   }
+  flush();
   return bad;
 }
 
@@ -227,27 +291,32 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   extern __shared__ uint8_t kms_smem_raw[];
   __shared__ __align__(8) uint64_t bar_t_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ int s_lab[BM];
+  __shared__ int s_lab[BM], s_old[BM];
   __shared__ float s_b1[BM], s_b2[BM];
   __shared__ int s_k1[BM];
-  __shared__ int s_amb[BM];
-  __shared__ int s_namb;
+  __shared__ int s_amb[BM], s_chg[BM];
+  __shared__ int s_namb, s_nchg, s_sorted;
+  __shared__ int s_cnt[kSmBN];
+  __shared__ unsigned char s_order[BM];
 
   const KmeansArgs& p = a.k;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const int dim = p.dim;
   const int K = p.num_clusters;
+  // image offsets in shared memory: every pass ends in a fence.acq_rel.gpu, which drops the L1
+  // lines, so reading them from global memory costs an L2 round trip per tile and pass
+  __shared__ int s_off[kSmMaxBatch + 1];
+  for (int i = tid; i <= p.batch; i += kGemmThreads)
+    s_off[i] = p.img_off ? p.img_off[i] : (i == 0 ? 0 : (int)p.rows_total);
+  __syncthreads();
   // every CTA takes a CONTIGUOUS range of the live tiles (image-major order)
   int live_total = 0;
-  for (int bb = 0; bb < p.batch; ++bb) {
-    const int64_t rows_b = p.img_off ? (int64_t)p.img_off[bb + 1] - p.img_off[bb] : p.rows_total;
-    live_total += (int)((rows_b + BM - 1) / BM);
-  }
+  for (int bb = 0; bb < p.batch; ++bb) live_total += (s_off[bb + 1] - s_off[bb] + BM - 1) >> 7;
   const int lt0 = (int)((int64_t)live_total * blockIdx.x / gridDim.x);
   const int lt1 = (int)((int64_t)live_total * (blockIdx.x + 1) / gridDim.x);
   const bool resident = live_total <= (int)gridDim.x;       // at most one tile per CTA: load it once
-  const size_t per_img = (size_t)K * dim;
+  const int per_img = K * dim;
   const size_t per_iter = (size_t)p.batch * per_img;
 
   // 1024-byte aligned carve-up by OFFSET, so that the pointers stay shared-space pointers
@@ -255,12 +324,15 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   uint8_t* a_hi = smem;                                        // [nkb][128 x 128 B]
   uint8_t* a_lo = a_hi + (size_t)a.nkb * kSmBlockBytes;
   uint8_t* b_tile = a_lo + (size_t)a.nkb * kSmBlockBytes;      // [nkb][hi | lo]
-  float* pf = reinterpret_cast<float*>(b_tile + (size_t)a.nkb * 2 * kSmBlockBytes);   // [K][dim]
-  int* s_hi = reinterpret_cast<int*>(pf + per_img);            // [K][dim]
+  // the tile's contribution to the sums as two int32 halves per entry; the same bytes stage
+  // the image's int64 totals while the prototypes are rebuilt (the halves are zero then)
+  int* s_hi = reinterpret_cast<int*>(b_tile + (size_t)a.nkb * 2 * kSmBlockBytes);   // [K][dim]
   int* s_lo = s_hi + per_img;
+  long long* s_tot = reinterpret_cast<long long*>(s_hi);
+  float* pf = reinterpret_cast<float*>(s_lo + per_img);        // [K][dim] fp32 prototypes
   float* xf = reinterpret_cast<float*>(
-      reinterpret_cast<uint8_t*>(s_lo + per_img) +
-      ((16u - (tc::smem_u32(s_lo + per_img) & 15u)) & 15u));   // 16-byte aligned (128-bit copies)
+      reinterpret_cast<uint8_t*>(pf + per_img) +
+      ((16u - (tc::smem_u32(pf + per_img) & 15u)) & 15u));     // 16-byte aligned (128-bit copies)
   const size_t xf_stride = (size_t)BM * dim + 4;               // a second buffer only with a.prefetch
   const float* xs = xf;   // xs[r * dim + d]: the fp32 tile, at the 16-byte phase of its source
 
@@ -272,7 +344,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   // operand tile: rows >= K and the K padding [dim, 64 nkb) must be zeros (0 x garbage = NaN)
   for (int i = tid; i < a.nkb * 2 * kSmBlockBytes / 16; i += kGemmThreads)
     reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < (int)per_img; i += kGemmThreads) s_hi[i] = 0, s_lo[i] = 0;
+  for (int i = tid; i < per_img; i += kGemmThreads) s_hi[i] = 0, s_lo[i] = 0;
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -290,17 +362,18 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   int cur = 0, lead_cur = 0, lead_nxt = 0;
   if (pf_on) {
     Tile first_tile;
-    kms_locate_tile(p, lt0, first_tile);
+    kms_locate_tile(s_off, lt0, first_tile);
     lead_cur = kms_prefetch_tile(p, first_tile, xf);
   }
+  bool bad = false;
 
   for (int it = 0; it <= p.iterations; ++it) {
     int proto_img = -1;    // image whose prototypes of pass it - 1 sit in shared memory
-    int pending = 0;       // tiles of the current image accumulated in s_hi / s_lo, not flushed
-    bool bad = false;
+    int pending = 0;       // tiles of the current image gathered in s_hi / s_lo, not flushed
     for (int lt = lt0; lt < lt1; ++lt) {
       Tile tile;
-      kms_locate_tile(p, lt, tile);
+      int img_base, tiles_b;
+      kms_locate_tile(s_off, lt, tile, &img_base, &tiles_b);
       const int b = tile.b;
       const int kb = p.k_per_image ? p.k_per_image[b] : K;
       KMS(0);
@@ -315,7 +388,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
           const int nlt = lt + 1 < lt1 ? lt + 1 : (it < p.iterations ? lt0 : -1);
           if (nlt >= 0) {
             Tile next;
-            kms_locate_tile(p, nlt, next);
+            kms_locate_tile(s_off, nlt, next);
             lead_nxt = kms_prefetch_tile(p, next, xf + (cur ^ 1) * xf_stride);
           }
         } else {
@@ -376,20 +449,28 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
       KMS(1);
 
       if (it == 0) {
+        // ================================================================== pass 0
         __syncthreads();
         if (tid < tile.rows) s_lab[tid] = p.labels_in[tile.row0 + tid];
-        __syncthreads();
+        // M-step over every row (the totals start here)
+        bad |= sort_rows_by_label(s_lab, tile.rows, kb, s_cnt, s_order, &s_sorted);
+        KMS(10);
+        KMS_SLOT_SWITCH(dim, (bad |= accumulate_tile<kS>(s_sorted, dim, xs, s_lab, s_order, s_hi,
+                                                         s_lo)));
+        if (!resident && tid < tile.rows) {
+          // the rows' labels travel through the output buffer between passes (same CTA)
+          if (p.labels_out) p.labels_out[tile.row0 + tid] = s_lab[tid];
+          else p.labels_out64[tile.row0 + tid] = s_lab[tid];
+        }
       } else {
         // ================================================================== E-step
         if (proto_img != b) {
           // ---- pass it - 1 of this image is complete once every one of its tiles is counted
           if (tid == 0) {
-            const int64_t rows_b = (int64_t)(p.img_off ? p.img_off[b + 1] - p.img_off[b]
-                                                       : p.rows_total);
-            const unsigned tiles_b = (unsigned)((rows_b + BM - 1) / BM);
             const unsigned* done = p.done + (size_t)(it - 1) * p.batch + b;
             unsigned spins = 0;
-            while (kms_ld_acquire_gpu(done) < tiles_b) {
+            while (kms_ld_acquire_gpu(done) < (unsigned)tiles_b) {
+              __nanosleep(40);   // ~100 pollers share this line with the CTAs still counting
               if (++spins > tc::kSpinLimit) {   // trap instead of hanging the GPU
                 printf("spml_b200: k-means pass %d of image %d never completed (block %d)\n",
                        it - 1, b, blockIdx.x);
@@ -400,12 +481,63 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
           }
           __syncthreads();
           KMS(2);
-          const long long* sums_prev = p.sums + (size_t)(it - 1) * p.replicas * per_iter + b * per_img;
-          KMS_SLOT_SWITCH(dim, (build_prototypes<kS, kKmReplicas>(p, sums_prev, per_iter, kb, pf,
-                                                                  b_tile)));
+          // ---- the image's totals after pass it - 1: one flat batch of L2 loads into the
+          // (currently all-zero) s_hi / s_lo bytes
+          // Every CTA of the image reads the SAME K x dim words at the same moment; walking
+          // them in the same order serialises ~100 SMs on a handful of L2 lines at a time
+          // (measured: 5-9k cycles for 19 KB).  Each CTA starts at its own rotation instead.
+          const long long* tot_prev = p.sums + (size_t)(it - 1) * per_iter + (size_t)b * per_img;
+          const int rot = (int)(((unsigned)blockIdx.x * 2654435761u >> 8) % (unsigned)per_img) & ~31;
+          for (int i0 = 0; i0 < per_img; i0 += 12 * kGemmThreads) {
+            long long r12[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              int i = i0 + j * kGemmThreads + tid;
+              const bool in = i < per_img;
+              i += rot;
+              i -= i >= per_img ? per_img : 0;
+              r12[j] = in ? __ldcg(tot_prev + i) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              int i = i0 + j * kGemmThreads + tid;
+              const bool in = i < per_img;
+              i += rot;
+              i -= i >= per_img ? per_img : 0;
+              if (in) s_tot[i] = r12[j];
+            }
+          }
+          __syncthreads();
+          KMS(11);
+          if (it < p.iterations) {
+            // ---- carry: the totals of pass it start from those of pass it - 1; every tile of
+            // the image brings over one slice (this CTA: the slices of its tiles of the image)
+            const int j0 = max(lt0, img_base) - img_base;
+            const int j1 = min(lt1, img_base + tiles_b) - img_base;
+            // (per_img <= 2^15 and tiles_b < 2^16 on every supported shape: 32-bit products)
+            const int c0 = (int)((unsigned)per_img * (unsigned)j0 / (unsigned)tiles_b);
+            const int c1 = (int)((unsigned)per_img * (unsigned)j1 / (unsigned)tiles_b);
+            long long* tot_it = p.sums + (size_t)it * per_iter + (size_t)b * per_img;
+            for (int i = c0 + tid; i < c1; i += kGemmThreads) {
+              const long long v = s_tot[i];
+              if (v != 0) atomic_add_i64(&tot_it[i], v);
+            }
+          }
+          KMS(12);
+          KMS_SLOT_SWITCH(dim, (build_prototypes<kS>(p, s_tot, kb, pf, b_tile)));
+          KMS(13);
+          __syncthreads();
+          for (int i = tid; i < per_img; i += kGemmThreads) s_hi[i] = 0, s_lo[i] = 0;
           proto_img = b;
         }
-        if (tid == 0) s_namb = 0;
+        // the labels of the previous pass (for the incremental M-step)
+        if (tid < BM) {
+          if (resident) s_old[tid] = s_lab[tid];
+          else if (tid < tile.rows)
+            s_old[tid] = p.labels_out ? p.labels_out[tile.row0 + tid]
+                                      : (int)p.labels_out64[tile.row0 + tid];
+        }
+        if (tid == 0) s_namb = 0, s_nchg = 0;
         tc::fence_proxy_async();   // generic-proxy stores (A and B operands) -> tensor core
         __syncthreads();
         KMS(3);
@@ -451,11 +583,11 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
             const int live = kb - cb;               // columns of this chunk that exist
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
-              float s = __uint_as_float(v[u]) + __uint_as_float(w[u]);
-              s = u < live ? s : -INFINITY;
-              b2 = fmaxf(b2, fminf(s, b1));         // second best so far (a tie counts)
-              k1 = s > b1 ? cb + u : k1;
-              b1 = fmaxf(b1, s);
+              float sc = __uint_as_float(v[u]) + __uint_as_float(w[u]);
+              sc = u < live ? sc : -INFINITY;
+              b2 = fmaxf(b2, fminf(sc, b1));        // second best so far (a tie counts)
+              k1 = sc > b1 ? cb + u : k1;
+              b1 = fmaxf(b1, sc);
             }
           }
         }
@@ -500,32 +632,58 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
         }
         __syncthreads();
         KMS(6);
-        if (it == p.iterations && tid < tile.rows) {
-          if (p.labels_out) p.labels_out[tile.row0 + tid] = s_lab[tid];
-          if (p.labels_out64) p.labels_out64[tile.row0 + tid] = s_lab[tid];
+        if (tid < tile.rows) {
+          const int lab = s_lab[tid];
+          if (!resident || it == p.iterations) {
+            if (p.labels_out) p.labels_out[tile.row0 + tid] = lab;
+            if (p.labels_out64 && (it == p.iterations || !p.labels_out))
+              p.labels_out64[tile.row0 + tid] = lab;
+          }
+          if (it < p.iterations && lab != s_old[tid]) s_chg[atomicAdd(&s_nchg, 1)] = tid;
+        }
+        if (it < p.iterations) {
+          // ================================================================ incremental M-step
+          __syncthreads();
+          const int nchg = s_nchg;
+          for (int i = warp; i < nchg; i += kSmWarps) {
+            const int r = s_chg[i];
+            const int to = s_lab[r] * dim, from = s_old[r];
+            for (int d = lane; d < dim; d += 32) {
+              const float v = xs[r * dim + d];
+              bad |= !(fabsf(v) <= 8.f);
+              int hi, lo;
+              split_fixed(v, hi, lo);
+              atomicAdd(&s_hi[to + d], hi);
+              atomicAdd(&s_lo[to + d], lo);
+              if ((unsigned)from < (unsigned)kb) {   // (a row whose initial label was invalid has
+                atomicAdd(&s_hi[from * dim + d], -hi);   //  nothing to take back)
+                atomicAdd(&s_lo[from * dim + d], -lo);
+              }
+            }
+          }
         }
       }
 
       if (it < p.iterations) {
-        // ================================================================== M-step
-        KMS_SLOT_SWITCH(dim, (bad |= accumulate_tile<kS>(tile.rows, dim, kb, xs, s_lab, s_hi, s_lo)));
         ++pending;
         bool flush = lt + 1 >= lt1 || pending >= kSmMaxTilesPerFlush;
         if (!flush) {
           Tile next;
-          kms_locate_tile(p, lt + 1, next);
+          kms_locate_tile(s_off, lt + 1, next);
           flush = next.b != b;
         }
         __syncthreads();
         KMS(7);
         if (flush) {
           // ---- non-zero entries -> the image's global sums (64-bit reductions), zero for reuse
-          long long* sums_b = p.sums + (size_t)it * p.replicas * per_iter + b * per_img +
-                              (size_t)(blockIdx.x % p.replicas) * per_iter;
-          for (int i = tid; i < (int)per_img; i += kGemmThreads) {
+          long long* tot_it = p.sums + (size_t)it * per_iter + (size_t)b * per_img;
+          const int rot = (int)(((unsigned)blockIdx.x * 2654435761u >> 8) % (unsigned)per_img) & ~31;
+          for (int i1 = tid; i1 < per_img; i1 += kGemmThreads) {
+            int i = i1 + rot;                 // staggered like the reads: spread the L2 lines
+            i -= i >= per_img ? per_img : 0;
             const int hi = s_hi[i], lo = s_lo[i];
             if ((hi | lo) != 0) {
-              atomic_add_i64(&sums_b[i], (long long)hi * 65536ll + lo);
+              atomic_add_i64(&tot_it[i], (long long)hi * 65536ll + lo);
               s_hi[i] = 0;
               s_lo[i] = 0;
             }
@@ -542,8 +700,8 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
       }
       if (pf_on) cur ^= 1, lead_cur = lead_nxt;
     }
-    if (bad) *p.poison = 1;
   }
+  if (bad) *p.poison = 1;
 
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -558,9 +716,10 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
 static bool kmeans_small_geometry(int dim, int num_clusters, int* nkb, int* prefetch, size_t* smem) {
   const int blocks = (dim + 63) / 64;
   if (dim < 1 || blocks > 2 || num_clusters < 1 || num_clusters > kSmBN) return false;
+  if (num_clusters * dim > (1 << 15)) return false;
   const size_t tile = ((size_t)BM * dim + 4) * sizeof(float);
   const size_t fixed = 1024 + (size_t)4 * blocks * kSmBlockBytes +            // A hi/lo, B hi/lo
-                       (size_t)num_clusters * dim * (sizeof(float) + 2 * sizeof(int)) + 64;
+                       (size_t)num_clusters * dim * (sizeof(float) + 2 * sizeof(int)) + 64;   // sums, fp32 rows
   if (fixed + tile > 220 * 1024) return false;
   *nkb = blocks;
   *prefetch = fixed + 2 * tile <= 220 * 1024;
@@ -568,9 +727,11 @@ static bool kmeans_small_geometry(int dim, int num_clusters, int* nkb, int* pref
   return true;
 }
 
-bool kmeans_small_supported(int dim, int num_clusters) {
+bool kmeans_small_supported(int dim, int num_clusters, int batch, int64_t rows) {
   int nkb, prefetch;
   size_t smem;
+  // (offsets are cached as int32 in shared memory; an image has fewer than 2^16 tiles)
+  if (batch > kSmMaxBatch || rows >= (1ll << 22) * batch || rows >= (1ll << 31)) return false;
   return kmeans_small_geometry(dim, num_clusters, &nkb, &prefetch, &smem);
 }
 
