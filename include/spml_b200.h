@@ -345,6 +345,12 @@ typedef struct spml_cluster_args {
   int32_t* kmeans_labels;       /* [cap] */
   int32_t* seed_out;            /* [cap] */
   int32_t* num_segments;        /* [1] */
+  /* The one host read-back of a step, inside the call (nullable: nothing is synchronised):
+     counts_host[0..2] = {rows kept, segments, *status}; *status (device word, nullable) is
+     reset to 0 once read.  The call then returns after `stream` has finished. */
+  int32_t* counts_host;         /* HOST pointer, [4] */
+  int32_t* status;              /* device word kernels OR error bits into */
+  int32_t* counts_dev;          /* device scratch [4] for the read-back (with counts_host) */
 } spml_cluster_args;
 
 size_t spml_segment_by_kmeans_workspace_bytes(int batch, int n, int dim_total, int num_clusters,

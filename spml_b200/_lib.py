@@ -55,6 +55,7 @@ class ClusterArgs(ctypes.Structure):
       ('sem_out', c_vp), ('inst_out', c_vp),
       ('dst', c_vp), ('img_off', c_vp), ('kmeans_labels', c_vp), ('seed_out', c_vp),
       ('num_segments', c_vp),
+      ('counts_host', c_vp), ('status', c_vp), ('counts_dev', c_vp),
   ]
 
 
@@ -196,6 +197,9 @@ def call(name, *args):
   return _call(lib, name, args)
 
 
+_fn_cache = {}
+
+
 def _call(lib, name, args):
   if PROFILE is not None:
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -217,13 +221,13 @@ def launch_count():
 
 
 def ptr(t):
-  """Device pointer of a CUDA tensor (None -> NULL)."""
+  """Device address of a CUDA tensor as an int (None -> NULL); ctypes converts it."""
   if t is None:
     return None
   if not t.is_cuda:
     raise RuntimeError('spml_b200 only runs on CUDA tensors (got a %s tensor); '
                        'there is no CPU path' % t.device.type)
-  return ctypes.c_void_p(t.data_ptr())
+  return t.data_ptr()
 
 
 class _Stream(ctypes.c_void_p):
@@ -232,8 +236,9 @@ class _Stream(ctypes.c_void_p):
 
 
 def stream_of(t):
-  s = _Stream(torch.cuda.current_stream(t.device).cuda_stream)
-  s.device = t.device
+  dev = t.device
+  s = _Stream(torch._C._cuda_getCurrentRawStream(dev.index))
+  s.device = dev
   return s
 
 

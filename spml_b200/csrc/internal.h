@@ -23,4 +23,39 @@ int topk_launch(const float* q, int64_t nq, const float* p, int64_t m, int dim,
                 const uint8_t* pvalid, int k, int64_t* topk_labels, int64_t* topk_index,
                 int32_t* hit_count, const TopkExtra& extra, cudaStream_t st);
 
+// segsort.cu --------------------------------------------------------------------------
+int segsort_fwd_partial(const spml_segsort_desc* d, float* stats, float* nll, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st, const float** partial_out,
+                        int* tiles_x_out);
+
+#ifdef __CUDACC__
+// The loss of one problem from the per-tile partial sums of its row losses (loss.py:149-190
+// reduction; SPML_REDUCE_* in the header).  Executed by ONE warp; every lane gets the value.
+__device__ inline float segsort_finalize_loss(const spml_segsort_desc& d,
+                                              const float* __restrict__ partial, int tiles_x) {
+  const int lane = threadIdx.x & 31;
+  float total = 0.f;
+  int nonempty = 0;
+  for (int g = 0; g < d.num_groups; ++g) {
+    float v = 0.f;
+    for (int x = lane; x < tiles_x; x += 32) v += partial[(size_t)g * tiles_x + x];
+    v = warp_sum(v);
+    if (d.reduction == SPML_REDUCE_GROUP_MEAN && d.group_off) {
+      const int ng = d.group_off[g + 1] - d.group_off[g];
+      if (ng > 0) {
+        total += v / (float)ng;
+        ++nonempty;
+      }
+    } else {
+      total += v;
+    }
+  }
+  if (d.reduction == SPML_REDUCE_SUM) return total;
+  if (d.reduction == SPML_REDUCE_GROUP_MEAN && d.group_off) return total / (float)nonempty;
+  const int64_t rows =
+      d.group_off ? (int64_t)d.group_off[d.num_groups] - d.group_off[0] : d.n_rows;
+  return total / (float)rows;
+}
+#endif
+
 }  // namespace spml

@@ -110,6 +110,17 @@ __global__ void cluster_key_kernel(const int32_t* __restrict__ km, const int64_t
   }
 }
 
+// {rows kept, segments, status} next to each other for ONE device->host copy; the status word
+// is handed over (reset) here
+__global__ void publish_counts_kernel(const int32_t* rows, const int32_t* segments, int32_t* status,
+                                      int32_t* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out[0] = *rows;
+  out[1] = *segments;
+  out[2] = status ? atomicExch(status, 0) : 0;
+  out[3] = 0;
+}
+
 constexpr int64_t kDroppedLabel = 0x7fffffffffffffffll;
 
 // resnet_deeplab.py:112-117 without the max-reduction: the label of a dropped pixel never
@@ -188,18 +199,6 @@ struct TagList {
   int n;
 };
 
-__global__ void pack_tag_list_kernel(TagList l, int col0, int col1, int64_t* __restrict__ masks) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= l.first[l.n]) return;
-  int s = 0;
-  while (s + 1 < l.n && i >= l.first[s + 1]) ++s;
-  const int64_t* row = l.src[s] + (i - l.first[s]) * l.ld[s];
-  unsigned long long m = 0;
-  for (int c = col0; c < col1; ++c)
-    if (row[c] != 0) m |= 1ull << (c - col0);
-  masks[i] = (int64_t)m;
-}
-
 __global__ void gather_mask_kernel(const int64_t* __restrict__ table, int64_t table_rows,
                                    const int64_t* __restrict__ index, int64_t rows,
                                    int64_t* __restrict__ out) {
@@ -219,6 +218,57 @@ __global__ void proto_flags_kernel(const int64_t* __restrict__ psem, int64_t m, 
   valid[i] = psem[i] < num_classes ? 1 : 0;
   if (fill_empty_masks && masks[i] == 0)
     masks[i] = num_classes >= 64 ? -1ll : (int64_t)((1ull << num_classes) - 1ull);
+}
+
+// One pass over everything the losses need besides the embeddings: the prototype bank of the
+// step (current prototypes + memory-bank entries, segsort.py:153-182) with its class labels,
+// labelled-prototype flags (segsort.py:184-194) and image-tag masks, and the per-pixel tag
+// masks (segsort.py:146-150).  Thread i serves element i of the bank matrix, prototype i and
+// pixel i.
+struct PrepArgs {
+  ConcatList protos;      // floats
+  ConcatList psem;        // int64
+  TagList ptags;          // rows of tag matrices (VOC heads)
+  const int64_t* img_tags;
+  int64_t img_tags_ld, tag_rows;
+  const int64_t* bid;
+  int64_t n, m_all, num_classes;
+  int dim, col0, col1, tag_mode;   // tag_mode 0: no masks, 1: image tags
+};
+
+__global__ void head_prep_kernel(PrepArgs a, float* __restrict__ p_all,
+                                 int64_t* __restrict__ psem_all, uint8_t* __restrict__ pvalid,
+                                 int64_t* __restrict__ pmask_all, int64_t* __restrict__ pix_mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.m_all * a.dim) {
+    int s = 0;
+    while (s + 1 < a.protos.n && i >= a.protos.first[s + 1]) ++s;
+    p_all[i] = reinterpret_cast<const float*>(a.protos.src[s])[i - a.protos.first[s]];
+  }
+  if (i < a.m_all) {
+    int s = 0;
+    while (s + 1 < a.psem.n && i >= a.psem.first[s + 1]) ++s;
+    const int64_t sem = reinterpret_cast<const int64_t*>(a.psem.src[s])[i - a.psem.first[s]];
+    psem_all[i] = sem;
+    pvalid[i] = sem < a.num_classes ? 1 : 0;
+    unsigned long long m = 0;
+    if (a.tag_mode == 1) {
+      const int64_t* row = a.ptags.src[s] + (i - a.ptags.first[s]) * a.ptags.ld[s];
+      for (int c = a.col0; c < a.col1; ++c)
+        if (row[c] != 0) m |= 1ull << (c - a.col0);
+    }
+    pmask_all[i] = (int64_t)m;
+  }
+  if (a.tag_mode == 1 && i < a.n) {
+    const int64_t img = a.bid[i];
+    unsigned long long m = 0;
+    if (img >= 0 && img < a.tag_rows) {
+      const int64_t* row = a.img_tags + img * a.img_tags_ld;
+      for (int c = a.col0; c < a.col1; ++c)
+        if (row[c] != 0) m |= 1ull << (c - a.col0);
+    }
+    pix_mask[i] = (int64_t)m;
+  }
 }
 
 // group g = image bid0 + g: first pixel row / first prototype column of each image (both
@@ -246,14 +296,25 @@ __global__ void group_offsets_kernel(const int64_t* __restrict__ bid, int64_t ro
   }
 }
 
-__global__ void head_finish_kernel(const float* __restrict__ raw, const int32_t* __restrict__ hits,
-                                   float w_ann, float w_occ, float w_sim, int k, unsigned enable,
+// the three losses from their per-tile partial sums (one warp each), weights, accuracy
+struct FinishArgs {
+  spml_segsort_desc desc[3];
+  const float* partial[3];
+  int tiles_x[3];
+};
+
+__global__ void head_finish_kernel(FinishArgs f, const int32_t* __restrict__ hits, float w_ann,
+                                   float w_occ, float w_sim, int k, unsigned enable,
                                    float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  out[0] = (enable & 1u) ? raw[0] * w_ann : 0.f;
-  out[1] = (enable & 2u) ? raw[1] * w_occ : 0.f;
-  out[2] = (enable & 4u) ? raw[2] * w_sim : 0.f;
-  out[3] = (enable & 8u) ? (float)hits[0] / ((float)hits[1] * (float)k) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 3) {
+    const float w = warp == 0 ? w_ann : (warp == 1 ? w_occ : w_sim);
+    float v = 0.f;
+    if (enable & (1u << warp)) v = segsort_finalize_loss(f.desc[warp], f.partial[warp], f.tiles_x[warp]) * w;
+    if (lane == 0) out[warp] = v;
+  } else if (lane == 0) {
+    out[3] = (enable & 8u) ? (float)hits[0] / ((float)hits[1] * (float)k) : 0.f;
+  }
 }
 
 __global__ void scale_grads_kernel(const float* g_ann, const float* g_occ, const float* g_sim,
@@ -514,6 +575,14 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
   SPML_LAUNCH_CHECK("cluster_key_kernel");
   SPML_TRY(spml_unique_inverse(key_hi, a->labels_out, cap, rows_dev, 0, a->segment_ids, nullptr,
                                nullptr, a->num_segments, nullptr, uq_ws, uq_bytes, stream));
+  if (a->counts_host) {
+    SPML_CHECK_ARG(a->counts_dev, "segment_by_kmeans: counts_host needs counts_dev");
+    publish_counts_kernel<<<1, 32, 0, st>>>(rows_dev, a->num_segments, a->status, a->counts_dev);
+    SPML_LAUNCH_CHECK("publish_counts_kernel");
+    SPML_CUDA(cudaMemcpyAsync(a->counts_host, a->counts_dev, 4 * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, st));
+    SPML_CUDA(cudaStreamSynchronize(st));
+  }
   return SPML_OK;
 }
 
@@ -560,9 +629,13 @@ int spml_gather_prototypes_fwd(const float* e, const float* el, int64_t rows, in
   SPML_TRY(spml_segment_prototypes_fwd(e, rows, nullptr, dim, seg, m, eps, protos, norms, ws0, b0,
                                        stream));
   if (p_sem || p_inst || p_batch) {
-    if (p_sem) SPML_CUDA(cudaMemsetAsync(p_sem, 0xff, (size_t)m * 8, st));
-    if (p_inst) SPML_CUDA(cudaMemsetAsync(p_inst, 0xff, (size_t)m * 8, st));
-    if (p_batch) SPML_CUDA(cudaMemsetAsync(p_batch, 0xff, (size_t)m * 8, st));
+    if (p_sem && p_inst == p_sem + m && p_batch == p_inst + m) {   // one [3, m] buffer: one fill
+      SPML_CUDA(cudaMemsetAsync(p_sem, 0xff, (size_t)m * 24, st));
+    } else {
+      if (p_sem) SPML_CUDA(cudaMemsetAsync(p_sem, 0xff, (size_t)m * 8, st));
+      if (p_inst) SPML_CUDA(cudaMemsetAsync(p_inst, 0xff, (size_t)m * 8, st));
+      if (p_batch) SPML_CUDA(cudaMemsetAsync(p_batch, 0xff, (size_t)m * 8, st));
+    }
     scatter_segment_labels_kernel<<<blocks_of(rows), 256, 0, st>>>(seg, batch, sem, inst, rows, m,
                                                                    p_sem, p_inst, p_batch, status);
     SPML_LAUNCH_CHECK("scatter_segment_labels_kernel");
@@ -619,6 +692,8 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
   const unsigned en = a->enable;
   const int64_t n = a->n, m_all = p.m_all;
   const bool contrast = (en & (kAnn | kOcc | kAcc)) != 0;
+  FinishArgs fin{};
+  for (int i = 0; i < 3; ++i) fin.desc[i] = p.desc[i];
 
   // ---- img_sim branch (side stream 0): per-image prototypes of its embeddings, then the loss
   SPML_TRY(fork_streams(*pool, st, 1));
@@ -628,22 +703,25 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
     SPML_TRY(spml_segment_prototypes_fwd(a->img_sim_on_plain ? a->e : a->el, n, nullptr, dsim,
                                          a->seg, a->m, a->eps, p.sim_protos, p.sim_norms,
                                          p.proto_ws, p.proto_ws_bytes, s0));
+    // the prototypes' instance labels (segsort.py:229-231 re-derives them per image): taken
+    // from the caller when it has them, else scattered from the pixels; either way every pixel
+    // must carry its segment's label (a violation is reported through the status word)
+    int32_t* status = a->status ? a->status : p.hits + 2;
     if (!a->pinst) {
       SPML_CUDA(cudaMemsetAsync(p.pinst, 0xff, (size_t)a->m * 8, s0));
       scatter_segment_labels_kernel<<<blocks_of(n), 256, 0, s0>>>(
-          a->seg, nullptr, nullptr, a->inst, n, a->m, nullptr, p.pinst, nullptr,
-          a->status ? a->status : p.hits + 2);
+          a->seg, nullptr, nullptr, a->inst, n, a->m, nullptr, p.pinst, nullptr, status);
       SPML_LAUNCH_CHECK("scatter_segment_labels_kernel");
-      check_segment_labels_kernel<<<blocks_of(n), 256, 0, s0>>>(
-          a->seg, nullptr, nullptr, a->inst, n, a->m, nullptr, p.pinst, nullptr,
-          a->status ? a->status : p.hits + 2);
-      SPML_LAUNCH_CHECK("check_segment_labels_kernel");
     }
+    check_segment_labels_kernel<<<blocks_of(n), 256, 0, s0>>>(
+        a->seg, nullptr, nullptr, a->inst, n, a->m, nullptr, a->pinst ? a->pinst : p.pinst,
+        nullptr, status);
+    SPML_LAUNCH_CHECK("check_segment_labels_kernel");
     group_offsets_kernel<<<(unsigned)ceil_div(a->max_groups + 1, 64), 64, 0, s0>>>(
         a->bid, n, a->pbid, a->m, a->max_groups, p.group_off, p.col_off, a->status);
     SPML_LAUNCH_CHECK("group_offsets_kernel");
-    SPML_TRY(spml_segsort_fwd(&p.desc[2], p.stats[2], nullptr, p.raw + 2, p.seg_ws[2],
-                              p.seg_ws_bytes[2], s0));
+    SPML_TRY(segsort_fwd_partial(&p.desc[2], p.stats[2], nullptr, p.seg_ws[2], p.seg_ws_bytes[2],
+                                 s0, &fin.partial[2], &fin.tiles_x[2]));
   }
 
   // ---- the prototype bank of this step: current prototypes + memory bank (segsort.py:153-182)
@@ -669,42 +747,40 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
     lp.first[cnt] = rows * a->dim;
     ll.first[cnt] = rows * a->dim_loc;
     ls.first[cnt] = lb.first[cnt] = lt.first[cnt] = rows;
-    concat_kernel<float><<<blocks_of(rows * a->dim), 256, 0, st>>>(lp, p.p_all);
-    SPML_LAUNCH_CHECK("concat_kernel");
-    concat_kernel<int64_t><<<blocks_of(rows), 256, 0, st>>>(ls, p.psem_all);
-    SPML_LAUNCH_CHECK("concat_kernel");
-    if (en & kOcc) {
-      if (a->nn_tags) {
-        // segsort_softmax_densepose.py:174-191: tags of a prototype = class of its most similar
-        // labelled prototype of the same image (>= threshold), no tag -> every tag
-        concat_kernel<float><<<blocks_of(rows * a->dim_loc), 256, 0, st>>>(ll, p.pl_all);
-        SPML_LAUNCH_CHECK("concat_kernel");
-        concat_kernel<int64_t><<<blocks_of(rows), 256, 0, st>>>(lb, p.pbid_all);
-        SPML_LAUNCH_CHECK("concat_kernel");
-        SPML_TRY(spml_nn_multiset_labels(p.pl_all, m_all, p.pl_all, m_all, a->dim_loc, p.psem_all,
-                                         p.pbid_all, p.pbid_all, (int)a->num_classes, 1,
-                                         a->nn_threshold, nullptr, p.pmask_all, p.nn_ws,
-                                         p.nn_ws_bytes, stream));
-      } else {
-        pack_tag_list_kernel<<<blocks_of(rows), 256, 0, st>>>(lt, a->tag_col0, a->tag_col1,
-                                                              p.pmask_all);
-        SPML_LAUNCH_CHECK("pack_tag_list_kernel");
-        SPML_TRY(spml_pack_tags(a->img_tags + a->tag_col0, a->tag_rows, a->tag_col1 - a->tag_col0,
-                                a->img_tags_ld, p.img_mask, stream));
-      }
-    } else {
-      SPML_CUDA(cudaMemsetAsync(p.pmask_all, 0, (size_t)m_all * 8, st));
-    }
-    proto_flags_kernel<<<blocks_of(m_all), 256, 0, st>>>(p.psem_all, m_all, a->num_classes,
-                                                         p.pvalid_ann, p.pmask_all,
-                                                         (en & kOcc) && a->nn_tags ? 1 : 0);
-    SPML_LAUNCH_CHECK("proto_flags_kernel");
-    if (en & kOcc) {
-      if (a->nn_tags)
-        gather_mask_kernel<<<blocks_of(n), 256, 0, st>>>(p.pmask_all, m_all, a->seg, n, p.pix_mask);
-      else
-        gather_mask_kernel<<<blocks_of(n), 256, 0, st>>>(p.img_mask, a->tag_rows, a->bid, n,
-                                                         p.pix_mask);
+    const bool voc_tags = (en & kOcc) && !a->nn_tags;
+    PrepArgs pa{};
+    pa.protos = lp;
+    pa.psem = ls;
+    pa.ptags = lt;
+    pa.img_tags = a->img_tags;
+    pa.img_tags_ld = a->img_tags_ld;
+    pa.tag_rows = a->tag_rows;
+    pa.bid = a->bid;
+    pa.n = n;
+    pa.m_all = m_all;
+    pa.num_classes = a->num_classes;
+    pa.dim = a->dim;
+    pa.col0 = a->tag_col0;
+    pa.col1 = a->tag_col1;
+    pa.tag_mode = voc_tags ? 1 : 0;
+    head_prep_kernel<<<blocks_of(std::max<int64_t>(rows * a->dim, n)), 256, 0, st>>>(
+        pa, p.p_all, p.psem_all, p.pvalid_ann, p.pmask_all, p.pix_mask);
+    SPML_LAUNCH_CHECK("head_prep_kernel");
+    if ((en & kOcc) && a->nn_tags) {
+      // segsort_softmax_densepose.py:174-191: tags of a prototype = class of its most similar
+      // labelled prototype of the same image (>= threshold), no tag -> every tag
+      concat_kernel<float><<<blocks_of(rows * a->dim_loc), 256, 0, st>>>(ll, p.pl_all);
+      SPML_LAUNCH_CHECK("concat_kernel");
+      concat_kernel<int64_t><<<blocks_of(rows), 256, 0, st>>>(lb, p.pbid_all);
+      SPML_LAUNCH_CHECK("concat_kernel");
+      SPML_TRY(spml_nn_multiset_labels(p.pl_all, m_all, p.pl_all, m_all, a->dim_loc, p.psem_all,
+                                       p.pbid_all, p.pbid_all, (int)a->num_classes, 1,
+                                       a->nn_threshold, nullptr, p.pmask_all, p.nn_ws,
+                                       p.nn_ws_bytes, stream));
+      proto_flags_kernel<<<blocks_of(m_all), 256, 0, st>>>(p.psem_all, m_all, a->num_classes,
+                                                           p.pvalid_ann, p.pmask_all, 1);
+      SPML_LAUNCH_CHECK("proto_flags_kernel");
+      gather_mask_kernel<<<blocks_of(n), 256, 0, st>>>(p.pmask_all, m_all, a->seg, n, p.pix_mask);
       SPML_LAUNCH_CHECK("gather_mask_kernel");
     }
 
@@ -715,8 +791,8 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
       SPML_CUDA(cudaStreamWaitEvent(s1, pool->fork, 0));
       SPML_TRY(spml_valid_scan(a->sem, 2, a->num_classes, nullptr, 1, (int)n, p.ann_dst, p.ann_rows,
                                p.ann_off, p.scan_ws, p.scan_ws_bytes, s1));
-      SPML_TRY(spml_segsort_fwd(&p.desc[0], p.stats[0], nullptr, p.raw + 0, p.seg_ws[0],
-                                p.seg_ws_bytes[0], s1));
+      SPML_TRY(segsort_fwd_partial(&p.desc[0], p.stats[0], nullptr, p.seg_ws[0],
+                                   p.seg_ws_bytes[0], s1, &fin.partial[0], &fin.tiles_x[0]));
     }
     if (en & kAcc) {
       cudaStream_t s2 = pool->side[2];
@@ -727,14 +803,14 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
                            p.hits, none, s2));
     }
     if (en & kOcc)
-      SPML_TRY(spml_segsort_fwd(&p.desc[1], p.stats[1], nullptr, p.raw + 1, p.seg_ws[1],
-                                p.seg_ws_bytes[1], stream));
+      SPML_TRY(segsort_fwd_partial(&p.desc[1], p.stats[1], nullptr, p.seg_ws[1],
+                                   p.seg_ws_bytes[1], st, &fin.partial[1], &fin.tiles_x[1]));
     if (en & kAnn) SPML_TRY(join_stream(*pool, 1, st));
     if (en & kAcc) SPML_TRY(join_stream(*pool, 2, st));
   }
   SPML_TRY(join_stream(*pool, 0, st));
-  head_finish_kernel<<<1, 32, 0, st>>>(p.raw, p.hits, a->weight_ann, a->weight_occ, a->weight_sim,
-                                       (int)std::min<int64_t>(5, m_all), en, out);
+  head_finish_kernel<<<1, 128, 0, st>>>(fin, p.hits, a->weight_ann, a->weight_occ, a->weight_sim,
+                                        (int)std::min<int64_t>(5, m_all), en, out);
   SPML_LAUNCH_CHECK("head_finish_kernel");
   return SPML_OK;
 }

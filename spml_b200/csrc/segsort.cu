@@ -16,6 +16,7 @@
 
 #include <algorithm>
 
+#include "internal.h"
 #include "segsort_tc.h"
 #include "tile_gemm.cuh"
 
@@ -181,33 +182,8 @@ segsort_fwd_kernel(spml_segsort_desc d, int dpad, float* __restrict__ stats,
 // loss[0] from the per-CTA partial sums, in a fixed order.
 __global__ void segsort_loss_finalize_kernel(spml_segsort_desc d, const float* __restrict__ partial,
                                              int tiles_x, float* __restrict__ loss) {
-  const int lane = threadIdx.x;  // one warp
-  float total = 0.f;
-  int nonempty = 0;
-  for (int g = 0; g < d.num_groups; ++g) {
-    float v = 0.f;
-    for (int x = lane; x < tiles_x; x += 32) v += partial[(size_t)g * tiles_x + x];
-    v = warp_sum(v);
-    if (d.reduction == SPML_REDUCE_GROUP_MEAN && d.group_off) {
-      const int ng = d.group_off[g + 1] - d.group_off[g];
-      if (ng > 0) {
-        total += v / (float)ng;
-        ++nonempty;
-      }
-    } else {
-      total += v;
-    }
-  }
-  if (lane != 0) return;
-  if (d.reduction == SPML_REDUCE_SUM) {
-    *loss = total;
-  } else if (d.reduction == SPML_REDUCE_GROUP_MEAN && d.group_off) {
-    *loss = total / (float)nonempty;
-  } else {
-    const int64_t rows =
-        d.group_off ? (int64_t)d.group_off[d.num_groups] - d.group_off[0] : d.n_rows;
-    *loss = total / (float)rows;
-  }
+  const float v = segsort_finalize_loss(d, partial, tiles_x);   // one warp
+  if (threadIdx.x == 0) *loss = v;
 }
 
 // ------------------------------------------------------------------------- backward
@@ -513,6 +489,45 @@ static int set_smem(Kernel k, size_t bytes, const char* who) {
 
 }  // namespace spml
 
+extern "C" size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d);
+
+namespace spml {
+
+// The forward without its last step: per-tile partial sums of the row losses are left in the
+// workspace (`*partial_out`, [num_groups][*tiles_x_out]); segsort_finalize_loss turns them
+// into the loss (internal.h).  The stage-group entry finishes its three losses in one kernel.
+int segsort_fwd_partial(const spml_segsort_desc* d, float* stats, float* nll, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st, const float** partial_out,
+                        int* tiles_x_out) {
+  int rc = check_desc(d, "segsort_fwd");
+  if (rc != SPML_OK) return rc;
+  SPML_CHECK_ARG(workspace && (stats || d->n_rows == 0), "segsort_fwd: null pointer");
+  if (workspace_bytes < spml_segsort_workspace_bytes(d)) {
+    set_error("segsort_fwd: workspace %zu < %zu bytes", workspace_bytes,
+              spml_segsort_workspace_bytes(d));
+    return SPML_E_WORKSPACE;
+  }
+  const int dpad = pad4(d->dim);
+  const int tiles_x = tiles_x_of(*d);
+  *tiles_x_out = tiles_x;
+  if (use_tc_path(*d)) {
+    const TcPlan plan = segsort_tc_plan(*d, workspace);
+    *partial_out = plan.partial;
+    return segsort_fwd_tc(*d, plan, stats, nll, st);
+  }
+  float* partial = reinterpret_cast<float*>(workspace);
+  *partial_out = partial;
+  const size_t smem = (size_t)dpad * (LDA + LDB) * sizeof(float);
+  rc = set_smem(segsort_fwd_kernel, smem, "segsort_fwd");
+  if (rc != SPML_OK) return rc;
+  dim3 grid((unsigned)tiles_x, (unsigned)d->num_groups);
+  segsort_fwd_kernel<<<grid, kGemmThreads, smem, st>>>(*d, dpad, stats, nll, partial);
+  SPML_LAUNCH_CHECK("segsort_fwd_kernel");
+  return SPML_OK;
+}
+
+}  // namespace spml
+
 extern "C" {
 
 size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
@@ -531,33 +546,13 @@ size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
 int spml_segsort_fwd(const spml_segsort_desc* d, float* stats, float* nll, float* loss,
                      void* workspace, size_t workspace_bytes, void* stream) {
   using namespace spml;
-  int rc = check_desc(d, "segsort_fwd");
+  SPML_CHECK_ARG(loss, "segsort_fwd: null pointer");
+  const float* partial = nullptr;
+  int tiles_x = 0;
+  int rc = segsort_fwd_partial(d, stats, nll, workspace, workspace_bytes, as_stream(stream),
+                               &partial, &tiles_x);
   if (rc != SPML_OK) return rc;
-  SPML_CHECK_ARG(loss && workspace && (stats || d->n_rows == 0), "segsort_fwd: null pointer");
-  if (workspace_bytes < spml_segsort_workspace_bytes(d)) {
-    set_error("segsort_fwd: workspace %zu < %zu bytes", workspace_bytes,
-              spml_segsort_workspace_bytes(d));
-    return SPML_E_WORKSPACE;
-  }
-  cudaStream_t st = as_stream(stream);
-  const int dpad = pad4(d->dim);
-  const int tiles_x = tiles_x_of(*d);
-  if (use_tc_path(*d)) {
-    const TcPlan plan = segsort_tc_plan(*d, workspace);
-    rc = segsort_fwd_tc(*d, plan, stats, nll, st);
-    if (rc != SPML_OK) return rc;
-    segsort_loss_finalize_kernel<<<1, 32, 0, st>>>(*d, plan.partial, tiles_x, loss);
-    SPML_LAUNCH_CHECK("segsort_loss_finalize_kernel");
-    return SPML_OK;
-  }
-  float* partial = reinterpret_cast<float*>(workspace);
-  const size_t smem = (size_t)dpad * (LDA + LDB) * sizeof(float);
-  rc = set_smem(segsort_fwd_kernel, smem, "segsort_fwd");
-  if (rc != SPML_OK) return rc;
-  dim3 grid((unsigned)tiles_x, (unsigned)d->num_groups);
-  segsort_fwd_kernel<<<grid, kGemmThreads, smem, st>>>(*d, dpad, stats, nll, partial);
-  SPML_LAUNCH_CHECK("segsort_fwd_kernel");
-  segsort_loss_finalize_kernel<<<1, 32, 0, st>>>(*d, partial, tiles_x, loss);
+  segsort_loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(*d, partial, tiles_x, loss);
   SPML_LAUNCH_CHECK("segsort_loss_finalize_kernel");
   return SPML_OK;
 }

@@ -23,7 +23,7 @@ def _f32c(t, name):
                        % (name, t.device))
   if t.dtype != torch.float32:
     raise TypeError('%s: expected float32, got %s' % (name, t.dtype))
-  return t.contiguous()
+  return t if t.is_contiguous() else t.contiguous()
 
 
 def _i64c(t, name):
@@ -32,7 +32,19 @@ def _i64c(t, name):
                        % (name, t.device))
   if t.dtype != torch.int64:
     t = t.long()
-  return t.contiguous()
+  return t if t.is_contiguous() else t.contiguous()
+
+
+_size_cache = {}
+
+
+def _cached_size(fn_name, *key):
+  """Workspace sizes only depend on the shape: one library call per distinct shape."""
+  k = (fn_name,) + key
+  v = _size_cache.get(k)
+  if v is None:
+    v = _size_cache[k] = int(getattr(_lib.load(), fn_name)(*key))
+  return v
 
 
 def _workspace(nbytes, device):
@@ -469,13 +481,12 @@ class SegmentByKmeansFn(torch.autograd.Function):
     DL = D + loc_ch
     seeds_c = _i64c(seeds, 'cluster_indices')
     seed_bs = 0 if seeds.dim() == 2 else n
-    lib = _lib.load()
     fbuf = torch.empty(cap * (D + DL + 2), dtype=torch.float32, device=dev)
     lbuf = torch.empty(cap * 5, dtype=torch.int64, device=dev)
-    head = (B + 2 + 3) // 4 * 4          # img_off [B + 1], num_segments [1]; keeps 16-byte alignment
+    head = (B + 2 + 4 + 3) // 4 * 4      # img_off [B + 1], num_segments [1], read-back scratch [4]
     ibuf = torch.empty(head + cap * 3, dtype=torch.int32, device=dev)
-    ws = _workspace(lib.spml_segment_by_kmeans_workspace_bytes(B, n, DL, int(num_k),
-                                                               int(iterations)), dev)
+    ws = _workspace(_cached_size('spml_segment_by_kmeans_workspace_bytes', B, n, DL, int(num_k),
+                                 int(iterations)), dev)
     a = _lib.ClusterArgs()
     a.emb, a.loc, a.loc_batch_stride = emb.data_ptr(), (loc_c.data_ptr() if loc_ch else None), loc_bs
     if labels is not None:
@@ -506,38 +517,49 @@ class SegmentByKmeansFn(torch.autograd.Function):
     a.img_off, a.num_segments = ip, ip + 4 * (B + 1)
     a.dst = ip + 4 * head
     a.kmeans_labels, a.seed_out = ip + 4 * (head + cap), ip + 4 * (head + 2 * cap)
-    status = status_word(dev)
+    # the one host synchronisation of the step happens inside the call: rows kept, segments
+    # and the pending error bits come back in one 16-byte copy
+    counts = (ctypes.c_int32 * 4)()
+    a.counts_host = ctypes.addressof(counts)
+    a.counts_dev = ip + 4 * (B + 2)
+    a.status = status_word(dev).data_ptr()
     call('spml_segment_by_kmeans', ctypes.byref(a), ptr(ws), ws.numel(), stream_of(emb))
-    # the one host synchronisation of the step: rows kept, segments, pending error bits
-    rows, segments, bits = torch.cat([ibuf[B:B + 2], status]).tolist()
-    raise_on_status(bits, dev)
+    rows, segments, bits = counts[0], counts[1], counts[2]
+    if bits:
+      raise RuntimeError('spml_b200 (reported by an earlier, asynchronous call): ' + '; '.join(
+          text for bit, text in _STATUS_TEXT.items() if bits & bit))
     e = torch.as_strided(fbuf, (rows, D), (D, 1), 0)
     el = torch.as_strided(fbuf, (rows, DL), (DL, 1), cap * D)
-    nx = torch.as_strided(fbuf, (rows,), (1,), cap * (D + DL))
-    nc = torch.as_strided(fbuf, (rows,), (1,), cap * (D + DL + 1))
-    lab, bid, cid = lbuf[:rows], lbuf[cap:cap + rows], lbuf[2 * cap:2 * cap + rows]
-    dst = ibuf[head:head + cap]
+    lab = torch.as_strided(lbuf, (rows,), (1,), 0)
+    bid = torch.as_strided(lbuf, (rows,), (1,), cap)
+    cid = torch.as_strided(lbuf, (rows,), (1,), 2 * cap)
     outs = [e, el, lab, cid, bid]
     if divisor:
-      outs += [lbuf[3 * cap:3 * cap + rows], lbuf[4 * cap:4 * cap + rows]]
-    ctx.save_for_backward(e, el, nx, nc, dst)
-    ctx.dims = (B, D, loc_ch, H, W)
+      outs += [torch.as_strided(lbuf, (rows,), (1,), 3 * cap),
+               torch.as_strided(lbuf, (rows,), (1,), 4 * cap)]
+    # the backward reads e, el, the two norms and the pixel -> row map: all inside these two
+    # buffers (kept whole; the addresses are re-derived from the dims)
+    ctx.save_for_backward(fbuf, ibuf)
+    ctx.dims = (B, D, loc_ch, H, W, head)
     ctx.mark_non_differentiable(*outs[2:])
     ctx.set_materialize_grads(False)
-    box.append((rows, segments, ibuf[:B + 1]))
+    box.append((rows, segments, ibuf))
     return tuple(outs)
 
   @staticmethod
   def backward(ctx, de, del_, *_):
-    e, el, nx, nc, dst = ctx.saved_tensors
-    B, D, loc_ch, H, W = ctx.dims
     if de is None and del_ is None:
       return (None,) * 14
-    demb = torch.empty(B, D, H, W, dtype=torch.float32, device=e.device)
+    fbuf, ibuf = ctx.saved_tensors
+    B, D, loc_ch, H, W, head = ctx.dims
+    cap, DL = B * H * W, D + loc_ch
+    demb = torch.empty(B, D, H, W, dtype=torch.float32, device=fbuf.device)
     de = _f32c(de, 'd(cluster_embedding)') if de is not None else None
     del_ = _f32c(del_, 'd(cluster_embedding_with_loc)') if del_ is not None else None
-    call('spml_normalize_pack_bwd', ptr(de), ptr(del_), ptr(e), ptr(el), ptr(nx), ptr(nc),
-         ptr(dst), B, D, loc_ch, H * W, EPS, ptr(demb), stream_of(e))
+    fp = fbuf.data_ptr()
+    call('spml_normalize_pack_bwd', ptr(de), ptr(del_), fp, fp + 4 * cap * D,
+         fp + 4 * cap * (D + DL), fp + 4 * cap * (D + DL + 1), ibuf.data_ptr() + 4 * head, B, D,
+         loc_ch, H * W, EPS, demb.data_ptr(), stream_of(fbuf))
     return (demb,) + (None,) * 13
 
 
@@ -552,32 +574,35 @@ class GatherPrototypesFn(torch.autograd.Function):
     rows, D, DL = e.shape[0], e.shape[1], el.shape[1]
     dev = e.device
     m = int(m)
-    lib = _lib.load()
     fbuf = torch.empty(m * (D + DL + 2), dtype=torch.float32, device=dev)
-    plab = torch.empty(3, m, dtype=torch.int64, device=dev)
-    ws = _workspace(lib.spml_gather_prototypes_workspace_bytes(m, D, DL), dev)
+    plab = torch.empty(3 * m, dtype=torch.int64, device=dev)
+    ws = _workspace(_cached_size('spml_gather_prototypes_workspace_bytes', m, D, DL), dev)
     protos = torch.as_strided(fbuf, (m, D), (D, 1), 0)
     protos_loc = torch.as_strided(fbuf, (m, DL), (DL, 1), m * D)
-    norms = torch.as_strided(fbuf, (m,), (1,), m * (D + DL))
-    norms_loc = torch.as_strided(fbuf, (m,), (1,), m * (D + DL + 1))
     cid, bid = _i64c(cid, 'cluster_indices'), _i64c(bid, 'batch_indices')
     sem, inst = _i64c(sem, 'semantic_labels'), _i64c(inst, 'instance_labels')
-    call('spml_gather_prototypes_fwd', ptr(e), ptr(el), rows, D, DL, ptr(cid), ptr(bid), ptr(sem),
-         ptr(inst), m, EPS, ptr(protos), ptr(protos_loc), ptr(norms), ptr(norms_loc),
-         ptr(plab[0]), ptr(plab[1]), ptr(plab[2]), ptr(status_word(dev)), ptr(ws), ws.numel(),
-         stream_of(e))
-    ctx.save_for_backward(protos, protos_loc, norms, norms_loc, cid)
-    p_sem, p_inst, p_bid = plab[0], plab[1], plab[2]
+    fp, lp = fbuf.data_ptr(), plab.data_ptr()
+    call('spml_gather_prototypes_fwd', e.data_ptr(), el.data_ptr(), rows, D, DL, cid.data_ptr(),
+         bid.data_ptr(), sem.data_ptr(), inst.data_ptr(), m, EPS, fp, fp + 4 * m * D,
+         fp + 4 * m * (D + DL), fp + 4 * m * (D + DL + 1), lp, lp + 8 * m, lp + 16 * m,
+         status_word(dev).data_ptr(), ws.data_ptr(), ws.numel(), stream_of(e))
+    ctx.save_for_backward(fbuf, cid)
+    ctx.dims = (m, D, DL)
+    p_sem = torch.as_strided(plab, (m,), (1,), 0)
+    p_inst = torch.as_strided(plab, (m,), (1,), m)
+    p_bid = torch.as_strided(plab, (m,), (1,), 2 * m)
     ctx.mark_non_differentiable(p_sem, p_inst, p_bid)
     ctx.set_materialize_grads(False)       # an unused prototype set costs nothing in the backward
     return protos, protos_loc, p_sem, p_inst, p_bid
 
   @staticmethod
   def backward(ctx, dp, dpl, *_):
-    protos, protos_loc, norms, norms_loc, cid = ctx.saved_tensors
-    rows, m = cid.shape[0], protos.shape[0]
-    D, DL = protos.shape[1], protos_loc.shape[1]
-    dev = protos.device
+    if dp is None and dpl is None:
+      return None, None, None, None, None, None, None
+    fbuf, cid = ctx.saved_tensors
+    m, D, DL = ctx.dims
+    rows = cid.shape[0]
+    dev = fbuf.device
     de = del_ = None
     if dp is not None:
       dp = _f32c(dp, 'd(prototypes)')
@@ -585,10 +610,10 @@ class GatherPrototypesFn(torch.autograd.Function):
     if dpl is not None:
       dpl = _f32c(dpl, 'd(prototypes_with_loc)')
       del_ = torch.empty(rows, DL, dtype=torch.float32, device=dev)
-    if dp is not None or dpl is not None:
-      call('spml_gather_prototypes_bwd', ptr(dp), ptr(dpl), ptr(protos), ptr(protos_loc),
-           ptr(norms), ptr(norms_loc), ptr(cid), rows, D, DL, m, EPS, ptr(de), ptr(del_),
-           stream_of(protos))
+    fp = fbuf.data_ptr()
+    call('spml_gather_prototypes_bwd', ptr(dp), ptr(dpl), fp, fp + 4 * m * D,
+         fp + 4 * m * (D + DL), fp + 4 * m * (D + DL + 1), cid.data_ptr(), rows, D, DL, m, EPS,
+         ptr(de), ptr(del_), stream_of(fbuf))
     return de, del_, None, None, None, None, None
 
 
@@ -697,10 +722,10 @@ class HeadLossFn(torch.autograd.Function):
     if e.shape[0] != a.n or protos.shape[0] != a.m:
       raise ValueError('embeddings / prototypes disagree with their label vectors')
     a.status = status_word(dev).data_ptr()
-    lib = _lib.load()
-    state = _workspace(lib.spml_head_workspace_bytes(ctypes.byref(a)), dev)
+    state = _workspace(_lib.load().spml_head_workspace_bytes(ctypes.byref(a)), dev)
     out = torch.empty(4, dtype=torch.float32, device=dev)
-    call('spml_head_fwd', ctypes.byref(a), ptr(state), state.numel(), ptr(out), stream_of(e))
+    call('spml_head_fwd', ctypes.byref(a), state.data_ptr(), state.numel(), out.data_ptr(),
+         stream_of(e))
     ctx.spec, ctx.state = spec, state
     ctx.save_for_backward(e, el, protos)
     ctx.set_materialize_grads(False)

@@ -141,7 +141,8 @@ class Segsort(nn.Module):
       groups, rows_per_group = int(bid[-1] - bid[0]) + 1, 0            # host sync
     spec = ops.HeadSpec(
         cid, datas['cluster_batch_index'], datas['cluster_semantic_label'],
-        datas['cluster_instance_label'], targets['prototype_semantic_label'], None,
+        datas['cluster_instance_label'], targets['prototype_semantic_label'],
+        targets.get('prototype_instance_label', None) if use_sim else None,
         targets['prototype_batch_index'], C, enable,
         (self.sem_ann_concentration, self.sem_occ_concentration, self.img_sim_concentration),
         (self.sem_ann_loss_weight, self.sem_occ_loss_weight, self.img_sim_loss_weight),
