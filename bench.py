@@ -59,6 +59,8 @@ def parse_args():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--repeats', type=int, default=0,
                   help='timed regions of --steps steps each (0: enough for ~1.2 s of load)')
+  ap.add_argument('--backbone-dtype', default='bf16', choices=['bf16', 'fp32'],
+                  help='train_* workloads: autocast dtype of the cuDNN backbone')
   ap.add_argument('--no-graph', action='store_true',
                   help='launch the kernels directly instead of replaying the CUDA graph (for ncu)')
   return ap.parse_args()
@@ -79,47 +81,86 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-  """nvidia-smi clocks / throttle reasons during the timed region."""
+  """SM clock and throttle reasons of one GPU during the timed region, every 100 ms, through
+  NVML in-process (nvidia_ml_py).  A looping `nvidia-smi` subprocess does the same job but its
+  queries stall the CUDA calls of the process that drives the sampled GPU (measured: +15 ms per
+  34 ms training step on rank 0 of a 2-GPU run), so it is only the fallback, at 500 ms."""
 
   QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
            'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+  # NVML clocks-event (throttle) reason bits
+  REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+             0x4: 'sw_power_cap'}
 
-  def __init__(self, gpu_index):
+  def __init__(self, gpu_index, period=0.1):
     super().__init__(daemon=True)
     self.gpu_index = gpu_index
-    self.rows = []
+    self.period = period
+    self.query_ms = []
+    self.rows = []            # (sm_mhz, max_mhz, reason bits or list of names)
     self.proc = None
+    self._stop_flag = threading.Event()
+    self.how = None
+
+  def _nvml_handle(self):
+    import pynvml
+    pynvml.nvmlInit()
+    uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+    if not uuid.startswith('GPU-'):
+      uuid = 'GPU-' + uuid
+    try:
+      return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+    except Exception:
+      return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
 
   def run(self):
     try:
+      nv, h = self._nvml_handle()
+      mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+      get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+          nv.nvmlDeviceGetCurrentClocksThrottleReasons
+      self.how = 'nvml'
+      while not self._stop_flag.is_set():
+        t0 = time.perf_counter()
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = int(get_reasons(h))
+        self.query_ms.append(1e3 * (time.perf_counter() - t0))
+        self.rows.append((float(sm), float(mx), [n for b, n in self.REASONS.items() if bits & b]))
+        self._stop_flag.wait(self.period)
+      return
+    except Exception:
+      pass
+    try:
+      self.how = 'nvidia-smi'
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '100'],
+           '--format=csv,noheader,nounits', '-lms', '500'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
       for line in self.proc.stdout:
-        self.rows.append([c.strip() for c in line.split(',')])
-    except Exception:       # nvidia-smi missing: report nothing rather than fail
+        r = [c.strip() for c in line.split(',')]
+        try:
+          self.rows.append((float(r[1]), float(r[2]),
+                            [n for n, v in zip(names, r[5:9]) if v.lower().startswith('active')]))
+        except (ValueError, IndexError):
+          continue
+    except Exception:       # neither NVML nor nvidia-smi: report nothing rather than fail
       pass
 
   def stop(self):
+    self._stop_flag.set()
     if self.proc is not None:
       self.proc.terminate()
-    sm, mx, reasons = [], [], set()
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for r in self.rows:
-      try:
-        sm.append(float(r[1]))
-        mx.append(float(r[2]))
-      except (ValueError, IndexError):
-        continue
-      for name, val in zip(names, r[5:9]):
-        if val.lower().startswith('active'):
-          reasons.add(name)
-    if not sm:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-    return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
-            'samples': len(sm)}
+    self.join(timeout=2.0)
+    if not self.rows:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'how': self.how}
+    sm = [r[0] for r in self.rows]
+    reasons = sorted({n for r in self.rows for n in r[2]})
+    return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(r[1] for r in self.rows),
+            'reasons': reasons, 'samples': len(sm), 'how': self.how,
+            'period_s': self.period,
+            'query_ms': round(statistics.median(self.query_ms), 3) if self.query_ms else None}
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -539,9 +580,231 @@ def run_b200(args):
     dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------ training step
+
+TRAIN_METRIC = 'training images/sec (512x512 crop, ResNet-101 DeepLab backbone + contrastive head)'
+
+
+def run_train(args):
+  """BASELINE.json metric, first clause: the whole training iteration of
+  pyscripts/train/train.py:154-293 on synthetic 512x512 images: ResNet-101 DeepLab backbone
+  (PyTorch / cuDNN, channels-last, bf16 autocast) -> contrastive head (libspml_b200, fp32) ->
+  backward -> ONE bucketed NCCL all-reduce of the 47.3 M backbone gradients (DDP, overlapped
+  with the backbone's backward) -> SGD step -> memory-bank update.  One process per GPU, the
+  minibatch sharded over the ranks (weak scaling: 4 images per GPU as shipped)."""
+  import torch.distributed as dist
+  from spml_b200 import _lib, ops
+  from spml_b200.backbone import ResnetDeeplabEmbedding, num_parameters
+  from spml_b200.head import ContrastiveHead
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      dist.init_process_group('nccl', device_id=dev)
+      dist.barrier()
+      torch.cuda.synchronize()
+    finally:
+      sys.stdout.flush()
+      os.dup2(saved, 1)
+      os.close(saved)
+  _lib.load()
+  w = synth.WORKLOADS[args.workload]
+  cfg = synth.make_config(w)
+  torch.manual_seed(235)
+  bf16 = args.backbone_dtype == 'bf16'
+  net = ResnetDeeplabEmbedding(w.dim).to(dev).to(memory_format=torch.channels_last)
+  n_params = num_parameters(net)
+  size = 4 * w.height      # 512: the embedding map is a quarter of the crop
+  graphed = not args.no_graph
+  if graphed:
+    # The backbone alone is ~1 000 cuDNN / ATen launches per step, i.e. launch-bound on the host
+    # (34 ms eager vs ~15 ms of GPU work at batch 4): its forward and backward are captured
+    # as two CUDA graphs (torch.cuda.make_graphed_callables); the head, the all-reduce and
+    # the optimizer stay outside the graphs.
+    sample = torch.randn(w.batch, 3, size, size, device=dev).contiguous(
+        memory_format=torch.channels_last)
+    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16, cache_enabled=False):
+      net = torch.cuda.make_graphed_callables(net, (sample,), num_warmup_iters=3)
+    del sample
+  model = net
+  if world > 1:
+    # bucket_cap_mb above the 190 MB of fp32 gradients: ONE NCCL all-reduce per step
+    model = torch.nn.parallel.DistributedDataParallel(
+        net, device_ids=[local_rank], gradient_as_bucket_view=True, broadcast_buffers=False,
+        bucket_cap_mb=256)
+  opt = torch.optim.SGD(net.parameters(), lr=3e-3, momentum=0.9, weight_decay=5e-4, fused=True)
+  head = ContrastiveHead(cfg, variant=w.variant).to(dev)
+  gen = torch.Generator().manual_seed(1000 + rank)
+  host = []
+  for s in range(4):
+    b = synth.make_batch(w, seed=235 + rank, step=s)
+    b['image'] = torch.randn(w.batch, 3, size, size, generator=gen)
+    host.append({k: v.pin_memory() for k, v in b.items() if k != 'embedding'})
+  keys = ('image', 'semantic_label', 'instance_label', 'semantic_tag', 'local_feature')
+  h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in keys)
+  loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+  phases = []     # per step: CUDA events at the phase boundaries (cheap; in every timed step)
+
+  def step(i, mark=None):
+    mark = mark if mark is not None else (lambda: None)
+    mark()
+    b = {k: host[i % 4][k].to(dev, non_blocking=True) for k in keys}
+    images = b['image'].contiguous(memory_format=torch.channels_last)
+    mark()
+    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16, cache_enabled=False):
+      emb = model(images)
+    mark()
+    out = head(emb.float(), b['semantic_label'], b['instance_label'], b['semantic_tag'],
+               b['local_feature'])
+    mark()
+    opt.zero_grad(set_to_none=True)
+    out['loss'].backward()          # DDP all-reduces the gradient bucket during this call
+    mark()
+    opt.step()
+    head.update_memory_bank(world)
+    zero = out['loss'].new_zeros(())
+    loss_host.copy_(torch.stack([out[k].detach() if out.get(k) is not None else zero for k in
+                                 ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss', 'accuracy')]),
+                    non_blocking=True)
+    mark()
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  warmup = max(args.warmup, 3)
+  # the sampler starts BEFORE the warm-up and the barrier: anything rank 0 does alone between
+  # the barrier and its first timed step is waiting time of the other ranks in the first
+  # all-reduce (a 0.3 s sleep here once showed up as +15 ms per step of a 20-step run)
+  sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get('SPML_BENCH_NO_SAMPLER') else None
+  if sampler:
+    sampler.start()
+  for i in range(warmup):
+    step(i)
+  barrier()
+  launches0 = _lib.launch_count()
+  pairs = []
+  for i in range(args.steps):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def mark():
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      marks.append(ev)
+    s.record()
+    step(warmup + i, mark)
+    e.record()
+    pairs.append((s, e))
+    phases.append(marks)
+  barrier()
+  clocks = sampler.stop() if sampler else None
+  launches = _lib.launch_count() - launches0
+  ms = sum(s.elapsed_time(e) for s, e in pairs)
+  names = ('h2d', 'backbone_forward', 'head_forward', 'backward_and_all_reduce', 'sgd_and_bank')
+  phase_ms = {n: sum(m[j].elapsed_time(m[j + 1]) for m in phases) / len(phases)
+              for j, n in enumerate(names)}
+  ops.check_status(dev)
+
+  # the gradient all-reduce alone (what DDP overlaps with the backward): flat fp32 buffer
+  allreduce, per_rank = None, None
+  if world > 1:
+    flat = torch.zeros(n_params, dtype=torch.float32, device=dev)
+    for _ in range(3):
+      dist.all_reduce(flat)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+      dist.all_reduce(flat)
+    e.record()
+    torch.cuda.synchronize()
+    ar_ms = s.elapsed_time(e) / 10
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {'ms_per_step': ms / args.steps, 'phase_ms': phase_ms})
+    t = torch.tensor([ms, ar_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0]), float(t[1])
+    gb = n_params * 4 / 1e9
+    allreduce = {'bytes': n_params * 4, 'ms': ar_ms, 'algbw_GBps': gb / (ar_ms * 1e-3),
+                 'busbw_GBps': gb / (ar_ms * 1e-3) * 2 * (world - 1) / world,
+                 'what': 'one NCCL all-reduce of the flat fp32 gradient, timed alone (the step issues '
+                         'the same all-reduce once, after the graphed backbone backward)'}
+  # the head's share of the step (same inputs, backbone output detached)
+  head_ms = None
+  if rank == 0:
+    b = {k: host[0][k].to(dev) for k in keys}
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+      emb0 = net(b['image'].contiguous(memory_format=torch.channels_last)).float()
+    bank = dict(head.memory_banks)
+    times = []
+    for _ in range(8):
+      head.memory_banks = dict(bank)
+      e_in = emb0.clone().requires_grad_(True)
+      s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s.record()
+      o = head(e_in, b['semantic_label'], b['instance_label'], b['semantic_tag'],
+               b['local_feature'])
+      o['loss'].backward()
+      e.record()
+      torch.cuda.synchronize()
+      times.append(s.elapsed_time(e))
+    head_ms = sorted(times)[len(times) // 2]
+  if rank == 0:
+    images = w.batch * world * args.steps
+    value = images / (ms * 1e-3)
+    line = {
+        'metric': TRAIN_METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16 backbone (autocast), f32 contrastive head' if bf16 else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': w.name, 'model': 'ResNet-101 DeepLab (47.3 M parameters, random '
+                   'init) + SPML contrastive head', 'images_per_gpu': w.batch,
+                   'global_batch': w.batch * world, 'crop': [size, size],
+                   'embedding_map': [w.height, w.width], 'embedding_dim': w.dim,
+                   'kmeans_seeds': list(w.num_clusters), 'kmeans_iterations': w.iterations,
+                   'memory_bank_steps': w.memory_bank_size,
+                   'parallelism': 'dp%d: one process per GPU, ONE NCCL all-reduce of the backbone '
+                                  'gradients per step (DDP, single 190 MB bucket), rank-local '
+                                  'prototypes' % world,
+                   'backbone_cuda_graphs': graphed,
+                   'l2': 'inputs + activations of a step exceed the 126 MB L2'},
+        'e2e': {'value': value, 'unit': 'images/s', 'ms_per_step': ms / args.steps,
+                'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 16,
+                'note': 'the timed step itself copies its images + labels from pinned host '
+                        'memory and reads the losses back'},
+        'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
+        'contrastive_head_ms': head_ms, 'phase_ms': phase_ms, 'all_reduce': allreduce,
+        'per_rank': per_rank if world > 1 else None,
+        'parameters': n_params,
+        'clocks': clocks,
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   args = parse_args()
-  if args.impl == 'reference':
+  if args.workload.startswith('train_'):
+    if args.impl == 'reference':
+      print(json.dumps({'impl': 'reference', 'unavailable':
+                        'the reference CPU training step (ResNet-101 at 512x512) takes minutes '
+                        'per step; the reference arm covers the contrastive-loss step workloads'}))
+      return
+    run_train(args)
+  elif args.impl == 'reference':
     run_reference(args)
   else:
     run_b200(args)

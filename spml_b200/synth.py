@@ -82,6 +82,11 @@ WORKLOADS = {
     # the softmax head train.py instantiates (segsort_softmax.py) at the VOC shapes
     'voc_scribble_softmax_b1': Workload(name='voc_scribble_softmax_b1', variant='softmax',
                                         label_upsample=4),
+    # BASELINE.json's first metric clause: the whole training step (ResNet-101 DeepLab backbone
+    # on cuDNN -> this head -> backward -> gradient all-reduce -> SGD) at the shipped per-GPU
+    # batch of 4 (bashscripts/voc12/train_spml_scribble.sh:28) and at batch 1; bench.py only.
+    'train_voc_b4': Workload(name='train_voc_b4', batch=4),
+    'train_voc_b1': Workload(name='train_voc_b1', batch=1),
     # small cases used by the parity tests / golden vectors.
     'tiny': Workload(name='tiny', batch=2, height=24, width=20, dim=16,
                      num_clusters=(3, 3), num_regions=9, iterations=10,
