@@ -505,6 +505,26 @@ def segsort_predictions(datas, targets):
   return torch.gather(pred, 0, cid), torch.index_select(topk, 0, cid)
 
 
+# --------------------------------------------------------------------------- f4
+
+
+def random_walk_cam(embedding_list, cam, walk_steps=6, power=20):
+  """pyscripts/inference/pseudo_softmaxrw_crf.py:135-170: affinities exp(5 cos - 5) of the
+  channel-normalised [1, C, h, w] embeddings (one per flip / scale, averaged), ** power,
+  column-normalised, squared walk_steps times, applied to the [classes, h, w] maps."""
+  affs = []
+  for embs in embedding_list:
+    embs = embs / torch.norm(embs, dim=1)
+    flat = embs.view(embs.shape[1], -1)
+    affs.append(torch.matmul(flat.t(), flat).mul_(5).add_(-5).exp_())
+  aff = torch.mean(torch.stack(affs, dim=0), dim=0)
+  aff_mat = aff ** power
+  trans = aff_mat / torch.sum(aff_mat, dim=0, keepdim=True)
+  for _ in range(walk_steps):
+    trans = torch.matmul(trans, trans)
+  return torch.matmul(cam.view(cam.shape[0], -1), trans).view(cam.shape)
+
+
 # --------------------------------------------------------------------------- step
 
 

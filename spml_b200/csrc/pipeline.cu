@@ -287,7 +287,9 @@ __global__ void group_offsets_kernel(const int64_t* __restrict__ bid, int64_t ro
     const int64_t* v = pass == 0 ? bid : pbid;
     const int64_t n = pass == 0 ? rows : m;
     int64_t lo = 0, hi = n;
-    if (g == groups) lo = n;       // the last group takes everything that is left
+    // rows: the last group takes everything that is left.  Columns: the bank may continue with
+    // the prototypes of other ranks' images (cross-GPU exchange), which belong to no group.
+    if (g == groups && pass == 0) lo = n;
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
       if (v[mid] < want) lo = mid + 1; else hi = mid;

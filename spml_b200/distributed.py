@@ -97,12 +97,13 @@ def all_reduce_gradients(parameters, bucket_bytes=64 << 20):
 
 # ------------------------------------------------------------------------------ SURVEY.md 8f-1
 #
-# Groundwork for the cross-GPU prototype exchange (the reference contrasts every pixel with
-# the prototypes of ALL GPUs and lets the gradient flow back, spml/models/utils.py:86-127).
-# Segments never span images, so a rank's prototypes are complete on that rank: the
-# exchange is an all-gather of fixed-capacity [M_cap, D] blocks (plus their labels), and
-# its backward a reduce-scatter of d(prototypes).  Not wired into the heads yet (PR1 uses
-# rank-local prototypes, north_star); the collective pair is tested on gloo.
+# Cross-GPU prototype exchange (the reference contrasts every pixel with the prototypes of
+# ALL GPUs and lets the gradient flow back, spml/models/utils.py:86-127).  Segments never span
+# images, so a rank's prototypes are complete on that rank: the exchange is an all-gather of
+# the ranks' [M_r, D] blocks (plus their labels), and its backward a reduce-scatter of
+# d(prototypes).  `exchange_prototypes` does it for the data-dependent M_r of the drop-in API;
+# ContrastiveHead(exchange_prototypes=True) uses it (default off: north_star's PR1 keeps
+# rank-local prototypes).
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -149,8 +150,59 @@ def all_gather_prototypes(prototypes, *labels, group=None):
   return tuple(gathered)
 
 
+def all_gather_rows(tensor, group=None):
+  """Non-differentiable all-gather of equally shaped row blocks (gather_and_update_datas,
+  spml/models/utils.py:134-154, for one process per GPU)."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return tensor
+  with torch.no_grad():
+    return _AllGatherRows.apply(tensor.detach(), group)
+
+
 def global_segment_ids(local_ids, m_cap, group=None):
   """Column of a pixel's own prototype in the gathered bank (negative ids stay negative)."""
   if not dist.is_initialized() or dist.get_world_size(group) == 1:
     return local_ids
   return torch.where(local_ids >= 0, local_ids + dist.get_rank(group) * int(m_cap), local_ids)
+
+
+def exchange_prototypes(prototypes, prototypes_with_loc, semantic_labels, instance_labels,
+                        batch_indices, cluster_indices, group=None):
+  """What spml/models/utils.py:86-127 gives every GPU, for one process per GPU: the prototypes
+  of ALL ranks (rank-major, i.e. ordered by global image index like the reference's sorted
+  ids), their labels, and this rank's pixel -> prototype ids moved into the global numbering.
+
+  One all-gather of the [M_r] counts (a host read-back: the result has a data-dependent
+  shape), one all-gather of the padded [M_max, D + D'] prototype rows and one of the padded
+  int64 label rows.  The prototypes stay differentiable: the backward reduce-scatters the
+  bank gradients, so a rank's pixels receive the gradient of every rank's loss, as in the
+  reference.  `batch_indices` must already be global (batch_index_offset = B * rank).
+  Returns (prototypes, prototypes_with_loc, semantic_labels, instance_labels, batch_indices,
+  cluster_indices).  A single process gets its inputs back."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return (prototypes, prototypes_with_loc, semantic_labels, instance_labels, batch_indices,
+            cluster_indices)
+  size, rank = dist.get_world_size(group), dist.get_rank(group)
+  dev = prototypes.device
+  m, d, dl = prototypes.shape[0], prototypes.shape[1], prototypes_with_loc.shape[1]
+  counts = torch.zeros(size, dtype=torch.int64, device=dev)
+  dist.all_gather_into_tensor(counts, torch.tensor([m], dtype=torch.int64, device=dev),
+                              group=group)
+  counts = counts.tolist()                                   # the exchange's host read-back
+  m_max = max(counts)
+  rows = torch.cat([prototypes, prototypes_with_loc], dim=1)
+  labels = torch.stack([semantic_labels, instance_labels, batch_indices], dim=1)
+  if m < m_max:
+    rows = torch.cat([rows, rows.new_zeros(m_max - m, d + dl)], dim=0)
+    labels = torch.cat([labels, labels.new_zeros(m_max - m, 3)], dim=0)
+  bank = _AllGatherRows.apply(rows, group)                   # [size * m_max, d + dl]
+  with torch.no_grad():
+    bank_labels = _AllGatherRows.apply(labels, group)
+  if any(c != m_max for c in counts):
+    keep = torch.cat([torch.arange(c) + r * m_max for r, c in enumerate(counts)]).to(dev)
+    bank = bank.index_select(0, keep)
+    bank_labels = bank_labels.index_select(0, keep)
+  offset = sum(counts[:rank])
+  return (bank[:, :d], bank[:, d:], bank_labels[:, 0].contiguous(),
+          bank_labels[:, 1].contiguous(), bank_labels[:, 2].contiguous(),
+          cluster_indices + offset)

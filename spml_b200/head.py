@@ -65,12 +65,17 @@ def generate_clusters_method(densepose=False):
 
 class ContrastiveHead(nn.Module):
 
-  def __init__(self, config, softmax_classifier=False, variant=None):
+  def __init__(self, config, softmax_classifier=False, variant=None, exchange_prototypes=False):
     """`variant`: 'segsort' (predictions/segsort.py), 'softmax' (segsort_softmax.py, the
     class train.py instantiates) or 'densepose' (resnet_pspnet_densepose.py clusters +
-    segsort_softmax_densepose.py, train_densepose.py:159-205)."""
+    segsort_softmax_densepose.py, train_densepose.py:159-205).
+    `exchange_prototypes`: under torch.distributed (one process per GPU) contrast this rank's
+    pixels with the prototypes of ALL ranks, gradients flowing back across ranks, which is
+    what the reference's anchor-GPU gather computes (spml/models/utils.py:86-127); image tags
+    are gathered like train.py:194-202.  Off: rank-local prototypes (north_star, PR1)."""
     super(ContrastiveHead, self).__init__()
     self.config = config
+    self.exchange_prototypes = bool(exchange_prototypes)
     self.variant = variant or ('softmax' if softmax_classifier else 'segsort')
     self.predictor = {'segsort': predictions.Segsort, 'softmax': predictions.SegsortSoftmax,
                       'densepose': predictions.SegsortSoftmaxDensepose}[self.variant](config)
@@ -84,17 +89,28 @@ class ContrastiveHead(nn.Module):
     """`semantic_label_full`: the full-resolution label map the classifier of the softmax
     variants is trained on (targets['semantic_label']); default: `semantic_label`."""
     cfg = self.config
+    exchange = (self.exchange_prototypes and torch.distributed.is_available()
+                and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1)
+    rank = torch.distributed.get_rank() if exchange else 0
     datas = generate_clusters(
         embedding, semantic_label, instance_label, local_feature, cfg.network.label_divisor,
         cfg.dataset.semantic_ignore_index, cfg.network.kmeans_num_clusters,
         cfg.network.kmeans_iterations,
-        batch_index_offset=0,   # rank-local image indices: `semantic_tag` is this rank's
+        # rank-local image indices (`semantic_tag` is this rank's) unless the prototypes of
+        # all ranks are exchanged: then global ones, like common.py:376-377's N * gpu_id
+        batch_index_offset=embedding.shape[0] * rank,
         densepose=self.variant == 'densepose')
     (protos, protos_loc, psem, pinst, pbid, cids) = (
         model_utils.gather_clustering_and_update_prototypes(
             [datas['cluster_embedding']], [datas['cluster_embedding_with_loc']],
             [datas['cluster_index']], [datas['cluster_batch_index']],
             [datas['cluster_semantic_label']], [datas['cluster_instance_label']]))
+    if exchange:
+      from . import distributed
+      protos, protos_loc, psem, pinst, pbid, cids = [[t] for t in distributed.exchange_prototypes(
+          protos[0], protos_loc[0], psem[0], pinst[0], pbid[0], cids[0])]
+      semantic_tag = distributed.all_gather_rows(semantic_tag)          # train.py:194-198
     datas['cluster_index'] = cids[0]
     datas['embedding'] = embedding
     targets = {'prototype': protos[0], 'prototype_with_loc': protos_loc[0],

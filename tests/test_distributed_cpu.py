@@ -101,3 +101,43 @@ def test_prototype_all_gather_single_process_is_identity():
   bank, bank_lab = D.all_gather_prototypes(x, lab)
   assert bank is x and bank_lab is lab
   assert D.global_segment_ids(lab, 3) is lab
+
+
+def _exchange_worker(rank, size, port, out):
+  os.environ.update(RANK=str(rank), WORLD_SIZE=str(size), LOCAL_RANK=str(rank),
+                    MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  D.init('gloo')
+  g = torch.Generator().manual_seed(11)
+  counts = [3, 5]                                  # data-dependent block sizes
+  protos = [torch.randn(c, 4, generator=g) for c in counts]
+  protos_loc = [torch.randn(c, 6, generator=g) for c in counts]
+  weights = [torch.randn(sum(counts), 4, generator=g) for _ in range(size)]
+  x = protos[rank].clone().requires_grad_(True)
+  xl = protos_loc[rank].clone().requires_grad_(True)
+  m = counts[rank]
+  sem, inst = torch.arange(m) + 10 * rank, torch.arange(m) + 100 * rank
+  bid = torch.full((m,), rank, dtype=torch.long)
+  cid = torch.tensor([0, m - 1, 1])
+  bank, bank_loc, gsem, ginst, gbid, gcid = D.exchange_prototypes(x, xl, sem, inst, bid, cid)
+  (bank * weights[rank]).sum().backward()
+  off = sum(counts[:rank])
+  want_grad = sum(w_[off:off + m] for w_ in weights)    # every rank's weights on the own block
+  out[rank] = (torch.allclose(bank.detach(), torch.cat(protos)),
+               torch.allclose(bank_loc.detach(), torch.cat(protos_loc)),
+               torch.allclose(x.grad, want_grad), gsem.tolist(), gbid.tolist(), gcid.tolist(),
+               xl.grad is None or float(xl.grad.abs().max()) == 0.0)
+  dist.destroy_process_group()
+
+
+def test_exchange_prototypes_variable_sizes():
+  """rank blocks of different sizes, rank-major bank, gradients of every rank's
+  loss reduce-scattered back to the owner."""
+  size, port = 2, _free_port()
+  with mp.Manager() as m:
+    out = m.dict()
+    mp.spawn(_exchange_worker, args=(size, port, out), nprocs=size, join=True)
+    r0, r1 = out[0], out[1]
+  for r in (r0, r1):
+    assert r[0] and r[1] and r[2] and r[6]
+    assert r[3] == [0, 1, 2, 10, 11, 12, 13, 14] and r[4] == [0, 0, 0, 1, 1, 1, 1, 1]
+  assert r0[5] == [0, 2, 1] and r1[5] == [3, 7, 4]

@@ -467,3 +467,55 @@ def test_calls_follow_the_tensor_device():
     y = general_common.normalize_embedding(x)
   assert y.device == x.device
   close(y, O.l2_normalize(x.cpu()), 1e-6)
+
+
+def test_memory_bank_files_and_retrieval(tmp_path, units2):
+  """the per-image .npy bank format (segsort/others.py:11-41) feeds
+  Segsort.predictions."""
+  from spml_b200 import predictions, segsort_others
+  u = units2['predictions']
+  half = u['bank'].shape[0] // 2
+  segsort_others.save_memory_bank(str(tmp_path / 'img_b.npy'), u['bank'][half:], u['bank_label'][half:])
+  segsort_others.save_memory_bank(str(tmp_path / 'img_a.npy'), u['bank'][:half], u['bank_label'][:half])
+  bank, labels = segsort_others.load_memory_banks(str(tmp_path), device='cuda')
+  assert torch.equal(bank.cpu(), u['bank']) and torch.equal(labels.cpu(), u['bank_label'])
+  model = predictions.segsort(synth.make_config(synth.WORKLOADS['tiny']))
+  pred, _ = model.predictions({'cluster_embedding': cu(u['emb']), 'cluster_index': cu(u['cid'])},
+                              {'semantic_memory_prototype': bank,
+                               'semantic_memory_prototype_label': labels})
+  assert torch.equal(pred.cpu(), u['pred'])
+
+
+def test_retrieval_at_inference_scale():
+  """f2 shape: 262 144 pixels (one 512 x 512 image at full resolution) in 576 segments against a
+  50 000-prototype bank, k = 20, vs the oracle's full argsort."""
+  g = torch.Generator().manual_seed(21)
+  n, segs, m, dim = 262144, 576, 50000, 64
+  centres = O.l2_normalize(torch.randn(200, dim, generator=g))
+  cid = torch.randint(0, segs, (n,), generator=g)
+  seg_centre = torch.randint(0, 200, (segs,), generator=g)
+  emb = O.l2_normalize(centres[seg_centre[cid]] + 0.4 * torch.randn(n, dim, generator=g))
+  bank_c = torch.randint(0, 200, (m,), generator=g)
+  bank = O.l2_normalize(centres[bank_c] + 0.4 * torch.randn(m, dim, generator=g))
+  bank_lab = bank_c % 21
+  want_pred, want_topk = O.segsort_predictions(
+      {'cluster_embedding': emb, 'cluster_index': cid},
+      {'semantic_memory_prototype': bank, 'semantic_memory_prototype_label': bank_lab})
+  from spml_b200 import predictions
+  model = predictions.segsort(synth.make_config(synth.WORKLOADS['tiny']))
+  pred, topk = model.predictions({'cluster_embedding': cu(emb), 'cluster_index': cu(cid)},
+                                 {'semantic_memory_prototype': cu(bank),
+                                  'semantic_memory_prototype_label': cu(bank_lab)})
+  assert float((topk.cpu() != want_topk).float().mean()) < 1e-3      # near-ties may swap
+  assert float((pred.cpu() != want_pred).float().mean()) < 1e-3
+
+
+def test_random_walk_matches_oracle():
+  """SURVEY.md 8f-4 (pseudo_softmaxrw_crf.py:135-170)."""
+  from spml_b200 import random_walk
+  g = torch.Generator().manual_seed(4)
+  embs = [torch.randn(1, 32, 24, 20, generator=g) for _ in range(2)]
+  cam = torch.rand(21, 24, 20, generator=g)
+  want = O.random_walk_cam(embs, cam, walk_steps=6)
+  got = random_walk.random_walk([random_walk.embedding_affinity(cu(e)) for e in embs], cu(cam), 6)
+  assert norm_err(got.cpu(), want) < 1e-4
