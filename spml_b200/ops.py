@@ -8,6 +8,7 @@ All arithmetic of the path happens inside libspml_b200.so.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -455,6 +456,30 @@ def check_status(device=None):
   raise_on_status(int(status_word(device)), device)
 
 
+# The ATen-side binding (csrc_torch/binding.cpp -> spml_b200/_C.so) does the same bookkeeping
+# as the ctypes code below in C++; it is used when it has been built (the build entry point
+# does) unless SPML_B200_BINDING=ctypes.  Both paths end in the same library calls.
+_C = None
+if os.environ.get('SPML_B200_BINDING', '') != 'ctypes':
+  try:
+    _lib.load()                      # libspml_b200.so first: _C.so links against it
+    from . import _C                 # noqa: F811
+    if _C.abi_version() != _lib.ABI_VERSION:
+      _C = None
+  except (ImportError, RuntimeError, OSError):
+    _C = None
+
+
+def binding():
+  """'aten' (C++ binding) or 'ctypes'."""
+  return 'aten' if _C is not None else 'ctypes'
+
+
+def _status_error(bits):
+  return RuntimeError('spml_b200 (reported by an earlier, asynchronous call): ' + '; '.join(
+      text for bit, text in _STATUS_TEXT.items() if bits & bit))
+
+
 class SegmentByKmeansFn(torch.autograd.Function):
   """segment_by_kmeans (spml/utils/segsort/common.py:270-408) as ONE library call and one
   host read-back (rows kept, segments, status).  Label packing of resnet_deeplab.py:112-117
@@ -464,6 +489,26 @@ class SegmentByKmeansFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, emb, loc, labels, sem, inst, divisor, semantic_ignore, ignore_index, seeds,
               k_per_image, num_k, iterations, batch_index_offset, box):
+    if _C is not None:
+      ignore_dev = ignore_index if torch.is_tensor(ignore_index) else None
+      outs, rows, segments, bits = _C.segment_fwd(
+          emb, loc, labels, sem, inst, int(divisor) if divisor else 0,
+          int(semantic_ignore) if semantic_ignore is not None else 0,
+          ignore_index is not None, 0 if (ignore_dev is not None or ignore_index is None)
+          else int(ignore_index), ignore_dev, seeds, k_per_image, int(num_k), int(iterations),
+          int(batch_index_offset), status_word(emb.device))
+      if bits:
+        raise _status_error(bits)
+      fbuf, ibuf = outs[-2], outs[-1]
+      outs = outs[:-2]
+      B, D, H, W = emb.shape
+      loc_ch = loc.shape[3] if loc is not None else 0
+      ctx.save_for_backward(fbuf, ibuf)
+      ctx.dims = (B, D, loc_ch, H, W, (B + 2 + 4 + 3) // 4 * 4)
+      ctx.mark_non_differentiable(*outs[2:])
+      ctx.set_materialize_grads(False)
+      box.append((rows, segments, ibuf))
+      return tuple(outs)
     emb = _f32c(emb, 'segment_by_kmeans(embeddings)')
     B, D, H, W = emb.shape
     n = H * W
@@ -526,8 +571,7 @@ class SegmentByKmeansFn(torch.autograd.Function):
     call('spml_segment_by_kmeans', ctypes.byref(a), ptr(ws), ws.numel(), stream_of(emb))
     rows, segments, bits = counts[0], counts[1], counts[2]
     if bits:
-      raise RuntimeError('spml_b200 (reported by an earlier, asynchronous call): ' + '; '.join(
-          text for bit, text in _STATUS_TEXT.items() if bits & bit))
+      raise _status_error(bits)
     e = torch.as_strided(fbuf, (rows, D), (D, 1), 0)
     el = torch.as_strided(fbuf, (rows, DL), (DL, 1), cap * D)
     lab = torch.as_strided(lbuf, (rows,), (1,), 0)
@@ -552,6 +596,8 @@ class SegmentByKmeansFn(torch.autograd.Function):
       return (None,) * 14
     fbuf, ibuf = ctx.saved_tensors
     B, D, loc_ch, H, W, head = ctx.dims
+    if _C is not None:
+      return (_C.segment_bwd(fbuf, ibuf, de, del_, B, D, loc_ch, H, W, head),) + (None,) * 13
     cap, DL = B * H * W, D + loc_ch
     demb = torch.empty(B, D, H, W, dtype=torch.float32, device=fbuf.device)
     de = _f32c(de, 'd(cluster_embedding)') if de is not None else None
@@ -569,6 +615,14 @@ class GatherPrototypesFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, e, el, cid, bid, sem, inst, m):
+    if _C is not None:
+      protos, protos_loc, p_sem, p_inst, p_bid, fbuf, cid_c = _C.gather_fwd(
+          e, el, cid, bid, sem, inst, int(m), status_word(e.device))
+      ctx.save_for_backward(fbuf, cid_c)
+      ctx.dims = (int(m), e.shape[1], el.shape[1])
+      ctx.mark_non_differentiable(p_sem, p_inst, p_bid)
+      ctx.set_materialize_grads(False)
+      return protos, protos_loc, p_sem, p_inst, p_bid
     e = _f32c(e, 'gather(embeddings)')
     el = _f32c(el, 'gather(embeddings_with_loc)')
     rows, D, DL = e.shape[0], e.shape[1], el.shape[1]
@@ -601,6 +655,9 @@ class GatherPrototypesFn(torch.autograd.Function):
       return None, None, None, None, None, None, None
     fbuf, cid = ctx.saved_tensors
     m, D, DL = ctx.dims
+    if _C is not None:
+      de, del_ = _C.gather_bwd(fbuf, cid, dp, dpl, m, D, DL)
+      return de, del_, None, None, None, None, None
     rows = cid.shape[0]
     dev = fbuf.device
     de = del_ = None
@@ -628,6 +685,20 @@ class HeadSpec:
                max_groups, max_rows_per_group=0, img_tags=None, ptags=None, tag_cols=(0, 0),
                bank=(), nn_tags=False, img_sim_on_plain=False, protos_loc=None,
                nn_threshold=0.95):
+    self.call = None
+    if _C is not None:
+      occ = bool(enable & ENABLE_OCC)
+      self.call = _C.HeadCall(
+          cid, bid, sem, inst, psem, pinst, pbid, int(num_classes), int(enable),
+          [float(k or 0.0) for k in kappas], [float(w or 0.0) for w in weights],
+          int(max_groups), int(max_rows_per_group), img_tags, ptags, int(tag_cols[0]),
+          int(tag_cols[1]), [b['prototype'] for b in bank], [b['semantic_label'] for b in bank],
+          [b['batch_index'] for b in bank],
+          [b['semantic_tag'] for b in bank] if (occ and not nn_tags) else [],
+          [b['prototype_with_loc'] for b in bank] if (occ and nn_tags) else [],
+          bool(nn_tags), bool(img_sim_on_plain), protos_loc, float(nn_threshold))
+      self.enable, self.img_sim_on_plain = int(enable), bool(img_sim_on_plain)
+      return
     self.keep = []
 
     def i64(t, name):
@@ -710,6 +781,13 @@ class HeadLossFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, e, el, protos, spec):
+    if spec.call is not None:
+      out = spec.call.forward(e, el, protos, status_word(e.device))
+      ctx.spec = spec
+      ctx.set_materialize_grads(False)
+      sem_ann, sem_occ, img_sim, acc = out.unbind(0)
+      ctx.mark_non_differentiable(acc)
+      return sem_ann, sem_occ, img_sim, acc
     e = _f32c(e, 'cluster_embedding')
     protos = _f32c(protos, 'prototype')
     a = spec.args
@@ -735,6 +813,12 @@ class HeadLossFn(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, g_ann, g_occ, g_sim, _g_acc):
+    if ctx.spec.call is not None:
+      if g_ann is None and g_occ is None and g_sim is None:
+        return None, None, None, None
+      need_e, need_el, need_p = ctx.needs_input_grad[:3]
+      de, del_, dprotos = ctx.spec.call.backward(g_ann, g_occ, g_sim, bool(need_p))
+      return (de if need_e else None), (del_ if need_el else None), dprotos, None
     e, el, protos = ctx.saved_tensors
     spec, state = ctx.spec, ctx.state
     a = spec.args

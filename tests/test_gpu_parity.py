@@ -92,3 +92,38 @@ def test_step_is_bit_reproducible():
   b = cuda_step(ContrastiveHead(cfg).cuda(), batch)
   for k in a:
     assert torch.equal(a[k], b[k]), k
+
+
+def test_both_host_bindings_give_the_same_step():
+  """The ATen (C++) binding and the ctypes binding are two bookkeeping layers over the same
+  library calls: a step through either gives bit-identical results."""
+  import json
+  import os
+  import subprocess
+  import sys
+  from conftest import ROOT
+  code = (
+      'import json, torch\n'
+      'from spml_b200 import ops, synth\n'
+      'from spml_b200.head import ContrastiveHead\n'
+      'w = synth.WORKLOADS["small"]; cfg = synth.make_config(w)\n'
+      'b = {k: v.cuda() for k, v in synth.make_batch(w).items()}\n'
+      'e = b["embedding"].clone().requires_grad_(True)\n'
+      'o = ContrastiveHead(cfg).cuda()(e, b["semantic_label"], b["instance_label"], '
+      'b["semantic_tag"], b["local_feature"])\n'
+      'o["loss"].backward()\n'
+      'print(json.dumps({"binding": ops.binding(), "loss": float(o["loss"]), '
+      '"acc": float(o["accuracy"]), "grad": float(e.grad.double().abs().sum()), '
+      '"ids": int(o["datas"]["cluster_index"].sum())}))\n')
+  got = {}
+  for binding in ('aten', 'ctypes'):
+    env = dict(os.environ, PYTHONPATH=ROOT, SPML_B200_BINDING=binding)
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr
+    got[binding] = json.loads(out.stdout.strip().splitlines()[-1])
+  assert got['ctypes']['binding'] == 'ctypes'
+  if got['aten']['binding'] != 'aten':
+    pytest.skip('spml_b200/_C.so is not built')
+  for k in ('loss', 'acc', 'grad', 'ids'):
+    assert got['aten'][k] == got['ctypes'][k], (k, got)
