@@ -3,6 +3,7 @@ build next to the product library:
     make -C spml_b200/csrc BUILD=build_trace TARGET=../libspml_b200_trace.so EXTRA=-DSPML_KM_TRACE
     SPML_B200_LIB=spml_b200/libspml_b200_trace.so python scripts/trace_kmeans_small.py [workload]"""
 import ctypes, os, sys
+os.environ['SPML_B200_BINDING'] = 'ctypes'   # the ATen binding links the product library, not the trace build
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spml_b200 import _lib, synth

@@ -74,3 +74,30 @@ def test_product_does_not_import_oracle():
   for fn in os.listdir(pkg):
     if fn.endswith('.py'):
       assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def integration_snippet():
+  text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+  blocks = re.findall(r'```python\n(.*?)```', text, flags=re.S)
+  return next(b for b in blocks if 'spml_segment_prototypes_fwd' in b)
+
+
+def test_integration_snippet_matches_the_header():
+  """The binding INTEGRATION.md shows a maintainer has as many arguments, in the same order of
+  pointer / integer / float kinds, as include/spml_b200.h declares."""
+  code = integration_snippet()
+  argtypes = re.search(r'spml_segment_prototypes_fwd\.argtypes = \[(.*?)\]', code).group(1)
+  kinds = [a.strip() for a in argtypes.split(',')]
+  header = open(os.path.join(ROOT, 'include', 'spml_b200.h')).read()
+  decl = re.search(r'int spml_segment_prototypes_fwd\((.*?)\);', header, flags=re.S).group(1)
+  params = [p.strip() for p in decl.replace('\n', ' ').split(',')]
+  assert len(kinds) == len(params) == 12
+
+  def kind(p):
+    if '*' in p:
+      return '_vp'
+    return {'int64_t': '_i64', 'int': '_i32', 'float': '_f32', 'size_t': '_sz'}[p.split()[0]]
+  assert kinds == [kind(p) for p in params]
+  assert [c_.__name__ for c_ in _lib.SIGNATURES['spml_segment_prototypes_fwd'][1]] == [
+      {'_vp': 'c_void_p', '_i64': 'c_long', '_i32': 'c_int', '_f32': 'c_float',
+       '_sz': 'c_ulong'}[k] for k in kinds]

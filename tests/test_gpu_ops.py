@@ -2,6 +2,7 @@
 golden unit vectors made by the reference and against the CPU oracle."""
 
 import ctypes
+import os
 
 import pytest
 import torch
@@ -519,3 +520,19 @@ def test_random_walk_matches_oracle():
   want = O.random_walk_cam(embs, cam, walk_steps=6)
   got = random_walk.random_walk([random_walk.embedding_affinity(cu(e)) for e in embs], cu(cam), 6)
   assert norm_err(got.cpu(), want) < 1e-4
+
+
+def test_integration_snippet_runs():
+  """The ctypes stub of INTEGRATION.md section 2, executed as written."""
+  import re
+  from conftest import ROOT
+  text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+  code = next(b for b in re.findall(r'```python\n(.*?)```', text, flags=re.S)
+              if 'spml_segment_prototypes_fwd' in b)
+  ns = {}
+  exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+  g = torch.Generator().manual_seed(8)
+  e = O.l2_normalize(torch.randn(300, 20, generator=g))
+  lab = torch.randint(0, 11, (300,), generator=g)
+  close(ns['calculate_prototypes_from_labels'](cu(e), cu(lab), 12),
+        O.prototypes_from_labels(e, lab, 12))
