@@ -291,6 +291,17 @@ __global__ void copy_labels_kernel(const int32_t* in, int64_t n, int32_t* out, i
   if (out64) out64[i] = in[i];
 }
 
+// The M-step saw an input outside the fixed-point range (|x| > 8 or NaN): the sums are
+// meaningless, so the ids are replaced by -1 (kmeans_small.cu does this in its last pass).
+__global__ void kmeans_poison_kernel(const int* __restrict__ poison, int64_t n,
+                                     int32_t* __restrict__ out, int64_t* __restrict__ out64) {
+  if (!*poison) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (out) out[i] = -1;
+  if (out64) out64[i] = -1;
+}
+
 static size_t kmeans_smem_bytes(int dpad) {
   return (size_t)dpad * (LDA + LDB) * sizeof(float);
 }
@@ -402,9 +413,16 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.eps = 1e-12f;
 
   if (path == kPathSmall) return kmeans_small_launch(p, sms, st);
-  if (use_tc)
-    return kmeans_tc_launch(p, base + kmeans_split_offset(batch, num_clusters, dim, iterations),
-                            sms, st);
+  const int64_t cap_rows = (int64_t)batch * max_rows_per_image;
+  if (use_tc) {
+    int rc = kmeans_tc_launch(p, base + kmeans_split_offset(batch, num_clusters, dim, iterations),
+                              sms, st);
+    if (rc != SPML_OK) return rc;
+    kmeans_poison_kernel<<<(unsigned)ceil_div(cap_rows, 256), 256, 0, st>>>(
+        p.poison, cap_rows, labels_out, labels_out_i64);
+    SPML_LAUNCH_CHECK("kmeans_poison_kernel");
+    return SPML_OK;
+  }
   const size_t smem = kmeans_smem_bytes(p.dpad);
   SPML_CUDA(cudaFuncSetAttribute(kmeans_persistent_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -417,6 +435,9 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   SPML_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kmeans_persistent_kernel),
                                         dim3(grid), dim3(kGemmThreads), args, smem, st));
   SPML_LAUNCH_CHECK("kmeans_persistent_kernel");
+  kmeans_poison_kernel<<<(unsigned)ceil_div(cap_rows, 256), 256, 0, st>>>(
+      p.poison, cap_rows, labels_out, labels_out_i64);
+  SPML_LAUNCH_CHECK("kmeans_poison_kernel");
   return SPML_OK;
 }
 

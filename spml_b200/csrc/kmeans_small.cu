@@ -633,7 +633,10 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
         __syncthreads();
         KMS(6);
         if (tid < tile.rows) {
-          const int lab = s_lab[tid];
+          int lab = s_lab[tid];
+          // an input outside the fixed-point range (|x| > 8, NaN) or an undeclared initial label
+          // was seen in an M-step: the sums are meaningless, say so instead of returning ids
+          if (it == p.iterations && *reinterpret_cast<volatile int*>(p.poison)) lab = -1;
           if (!resident || it == p.iterations) {
             if (p.labels_out) p.labels_out[tile.row0 + tid] = lab;
             if (p.labels_out64 && (it == p.iterations || !p.labels_out))
@@ -672,8 +675,9 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
           kms_locate_tile(s_off, lt + 1, next);
           flush = next.b != b;
         }
-        __syncthreads();
+        const bool any_bad = __syncthreads_or(bad);
         KMS(7);
+        if (any_bad && tid == 0) *p.poison = 1;   // published before this pass is counted
         if (flush) {
           // ---- non-zero entries -> the image's global sums (64-bit reductions), zero for reuse
           long long* tot_it = p.sums + (size_t)it * per_iter + (size_t)b * per_img;
@@ -701,8 +705,6 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
       if (pf_on) cur ^= 1, lead_cur = lead_nxt;
     }
   }
-  if (bad) *p.poison = 1;
-
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {

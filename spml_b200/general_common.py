@@ -32,8 +32,9 @@ def one_hot(labels, max_label=None):
 
 
 def segment_mean(x, index):
-  """spml/utils/general/common.py:123-147 (tf.segment_mean): the segment sums run
-  through the same fixed-point kernel as the prototypes, un-normalised."""
+  """spml/utils/general/common.py:123-147 (tf.segment_mean).  Not on the training path (its
+  only caller is pyscripts/inference/pseudo_denseposerw_crf.py:172): plain library scatter-adds
+  on the device, same arithmetic as the reference."""
   x = x.view(-1, x.shape[-1])
   index = index.view(-1)
   m = int(index.max()) + 1

@@ -74,6 +74,12 @@ def kmeans_with_initial_labels(embeddings, initial_labels, max_label=None, itera
   img_off = torch.tensor([0, n], dtype=torch.int32, device=x.device)
   init = initial_labels.reshape(-1).to(torch.int32)
   _, out64 = ops.kmeans(x, img_off, 1, n, max_label, iterations, init)
+  # The segment sums are 2^-32 fixed point and need |x| <= 8 (unit vectors on the training
+  # path); the kernels flag anything else (also NaN and labels >= max_label) and return -1
+  # ids.  The reference synchronises here as well (`.max()`), so the check costs nothing new.
+  if n > 0 and int(out64.min()) < 0:
+    raise ValueError('kmeans_with_initial_labels: embeddings must be finite with |x| <= 8 and '
+                     'initial labels in [0, max_label)')
   return out64
 
 

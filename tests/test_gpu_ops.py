@@ -536,3 +536,21 @@ def test_integration_snippet_runs():
   lab = torch.randint(0, 11, (300,), generator=g)
   close(ns['calculate_prototypes_from_labels'](cu(e), cu(lab), 12),
         O.prototypes_from_labels(e, lab, 12))
+
+
+@pytest.mark.parametrize('path', ['small', 'tc', 'fp32'])
+def test_kmeans_rejects_inputs_outside_the_fixed_point_range(path, monkeypatch):
+  """the segment sums are 2^-32 fixed point (|x| <= 8); anything else used to give
+  silently wrong labels.  Every kernel now flags it and the wrapper raises."""
+  monkeypatch.setenv('SPML_B200_KMEANS', path)
+  g = torch.Generator().manual_seed(2)
+  e = O.l2_normalize(torch.randn(600, 20, generator=g))
+  lab0 = torch.randint(0, 6, (600,), generator=g)
+  ok = segsort_common.kmeans_with_initial_labels(cu(e), cu(lab0), 6, 3)
+  assert int(ok.min()) >= 0
+  bad = e.clone()
+  bad[17, 3] = float('nan')
+  with pytest.raises(ValueError, match='finite'):
+    segsort_common.kmeans_with_initial_labels(cu(bad), cu(lab0), 6, 3)
+  with pytest.raises(ValueError, match='finite'):
+    segsort_common.kmeans_with_initial_labels(cu(e * 100.0), cu(lab0), 6, 3)
