@@ -284,7 +284,11 @@ def algorithmic_work(key, sh):
                            prob, (n, sh['m_all'], d))
     if name == 'spml_segsort_fwd':
       return (rows * (dim * 4 + 36) + cols * dim * 4, 2 * rows * cols * dim)
-    return (rows * (2 * dim * 4 + dim * 4 + 36) + 3 * cols * dim * 4, 6 * rows * cols * dim)
+    # backward: S again, d(embedding), and d(prototypes) of the CURRENT step's columns only
+    # (the memory-bank columns of sem_ann / sem_occ are detached: no gradient is computed)
+    gcols = cols if prob == 'img_sim' else cols * sh['m_cur'] / max(sh['m_all'], 1)
+    return (rows * (2 * dim * 4 + dim * 4 + 36) + (2 * cols + gcols) * dim * 4,
+            (4 * cols + 2 * gcols) * rows * dim)
   if name == 'spml_segment_prototypes_fwd':
     return (n * d * 4 + n * 8 + 3 * sh['m_cur'] * d * 4, 2 * n * d)
   if name == 'spml_segment_prototypes_bwd':
@@ -504,6 +508,7 @@ def run_b200(args):
     records, _lib.PROFILE = _lib.PROFILE, None
     agg = {}
     for name, s, e, kernels in records:
+      name = name.replace('spml_segsort_bwd_rows', 'spml_segsort_bwd')   # same kernels
       a = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'kernels': 0})
       a['ms'] += s.elapsed_time(e)
       a['calls'] += 1

@@ -259,6 +259,13 @@ int spml_segsort_bwd(const spml_segsort_desc* desc, const float* stats,
                      const float* grad_loss, float beta, float* demb, int64_t ld_demb,
                      float* dprotos, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* The same with the prototype gradient limited to the first dprotos_rows prototypes
+ * (dprotos is [dprotos_rows, dim]): the rows behind them are a detached memory bank
+ * (train.py:276-293), whose gradient the reference computes and throws away. */
+int spml_segsort_bwd_rows(const spml_segsort_desc* desc, const float* stats,
+                          const float* grad_loss, float beta, float* demb, int64_t ld_demb,
+                          float* dprotos, int64_t dprotos_rows, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* packs rows of a [rows, cols] int64 0/1 matrix (cols <= 64, row stride ld) into
  * bit masks: bit c set iff tags[r, c] != 0  (loss.py:107-109 uses (a.b) > 0). */
@@ -394,10 +401,12 @@ int spml_gather_prototypes_bwd(const float* dprotos, const float* dprotos_loc, c
  *               violation sets bit 2 of status[0] (nullable).
  *       wide_tags: more than 32 tag columns (keeps sem_occ off the tcgen05 kernels, whose
  *               epilogue compares 32-bit codes).
- *     fwd writes out[0..3] = {w_ann sem_ann, w_occ sem_occ, w_sim img_sim, accuracy} and
+ *     fwd writes out[0..4] = {w_ann sem_ann, w_occ sem_occ, w_sim img_sim, accuracy, the
+ *     sum of the enabled losses in that order (train.py:213-219)} and
  *     leaves what the backward needs in `state` (spml_head_workspace_bytes(args),
- *     256-byte aligned, untouched between the two calls).  bwd takes the three incoming
- *     gradients as device scalars (NULL = zero) and writes de [n, dim], del [n, dim_loc]
+ *     256-byte aligned, untouched between the two calls).  bwd takes the incoming gradients
+ *     of the three losses and of their sum as device scalars (NULL = zero; g_total counts
+ *     for every enabled loss) and writes de [n, dim], del [n, dim_loc]
  *     (nullable when unused) and dprotos [m, dim] (nullable; memory-bank prototypes are
  *     detached, train.py:280).
  */
@@ -440,8 +449,8 @@ size_t spml_head_workspace_bytes(const spml_head_args* args);
 int spml_head_fwd(const spml_head_args* args, void* state, size_t state_bytes, float* out,
                   void* stream);
 int spml_head_bwd(const spml_head_args* args, void* state, size_t state_bytes,
-                  const float* g_ann, const float* g_occ, const float* g_sim, float* de,
-                  float* del, float* dprotos, void* stream);
+                  const float* g_ann, const float* g_occ, const float* g_sim,
+                  const float* g_total, float* de, float* del, float* dprotos, void* stream);
 
 #ifdef __cplusplus
 }

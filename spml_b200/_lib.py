@@ -117,6 +117,8 @@ SIGNATURES = {
                                         c_sz, c_vp]),
     'spml_segsort_bwd': (ctypes.c_int, [ctypes.POINTER(SegsortDesc), c_vp, c_vp, c_f32, c_vp,
                                         c_i64, c_vp, c_vp, c_sz, c_vp]),
+    'spml_segsort_bwd_rows': (ctypes.c_int, [ctypes.POINTER(SegsortDesc), c_vp, c_vp, c_f32, c_vp,
+                                             c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
     'spml_pack_tags': (ctypes.c_int, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
     'spml_topk_ranking': (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                          c_i32, c_vp, c_vp, c_vp, c_vp]),
@@ -135,7 +137,7 @@ SIGNATURES = {
     'spml_head_workspace_bytes': (c_sz, [ctypes.POINTER(HeadArgs)]),
     'spml_head_fwd': (ctypes.c_int, [ctypes.POINTER(HeadArgs), c_vp, c_sz, c_vp, c_vp]),
     'spml_head_bwd': (ctypes.c_int, [ctypes.POINTER(HeadArgs), c_vp, c_sz, c_vp, c_vp, c_vp, c_vp,
-                                     c_vp, c_vp, c_vp]),
+                                     c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lock = threading.Lock()

@@ -27,6 +27,15 @@ int topk_launch(const float* q, int64_t nq, const float* p, int64_t m, int dim,
 int segsort_fwd_partial(const spml_segsort_desc* d, float* stats, float* nll, void* workspace,
                         size_t workspace_bytes, cudaStream_t st, const float** partial_out,
                         int* tiles_x_out);
+// backward with d(prototypes) limited to the first `proto_rows` prototypes and, with
+// `partial_out`, left as [*chunks_out][proto_rows][dim] partial sums in the workspace
+int segsort_bwd_impl(const spml_segsort_desc* d, const float* stats, const float* grad_loss,
+                     float beta, float* demb, int64_t ld_demb, float* dprotos, int64_t proto_rows,
+                     const float** partial_out, int* chunks_out, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st);
+// out[i] = sum over the chunks of pa and pb (either may have 0 chunks)
+int segsort_reduce_two(const float* pa, int ca, const float* pb, int cb, int64_t count, float* out,
+                       cudaStream_t st);
 
 #ifdef __CUDACC__
 // The loss of one problem from the per-tile partial sums of its row losses (loss.py:149-190

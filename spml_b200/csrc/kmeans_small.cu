@@ -28,7 +28,7 @@
 
 namespace spml {
 
-constexpr int kSmBN = 128;                 // prototype rows of the operand tile
+constexpr int kSmBN = 128;                 // most prototype rows of the operand tile (64 when K <= 64)
 constexpr int kSmBlockBytes = 128 * 128;   // one 64-wide K block of a 128-row bf16 tile
 constexpr int kSmWarps = kGemmThreads / 32;
 constexpr int kSmMaxBatch = 255;           // images per call (offsets cached in shared memory)
@@ -49,6 +49,7 @@ struct KmeansSmallArgs {
   int nkb;        // 64-wide K blocks
   int ksteps;     // 16-wide K steps that hold data
   int prefetch;   // a second fp32 tile buffer fits
+  int bn;         // prototype rows of the operand tile: 64 or 128 (UMMA N = bn and 2 bn)
   float tau;
 };
 
@@ -69,11 +70,12 @@ __device__ __forceinline__ void kms_cp_async_4(void* dst, const void* src) {
                : "memory");
 }
 
-// byte offset of element (row, d) inside a [nkb][hi | lo] SWIZZLE_128B operand: what a TMA
-// box {64 bf16, 128 rows} would write (tc_common.cuh)
-__device__ __forceinline__ uint32_t operand_offset(int row, int d) {
+// byte offset of element (row, d) inside a [nkb][hi | lo] SWIZZLE_128B operand whose hi and lo
+// parts are `part_bytes` (= rows * 128) each: what a TMA box {64 bf16, rows} would write
+// (tc_common.cuh)
+__device__ __forceinline__ uint32_t operand_offset(int row, int d, uint32_t part_bytes) {
   const uint32_t sw = row & 7;
-  return (uint32_t)(d >> 6) * (2 * kSmBlockBytes) + (uint32_t)(row >> 3) * 1024 + sw * 128 +
+  return (uint32_t)(d >> 6) * (2 * part_bytes) + (uint32_t)(row >> 3) * 1024 + sw * 128 +
          (((((uint32_t)d & 63) >> 3) ^ sw) << 4) + ((uint32_t)d & 7) * 2;
 }
 
@@ -124,7 +126,8 @@ template <int kSlots>
 __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
                                                  const long long* __restrict__ totals, int kb,
                                                  float* __restrict__ pf,
-                                                 uint8_t* __restrict__ b_tile) {
+                                                 uint8_t* __restrict__ b_tile,
+                                                 uint32_t b_part) {
   // kC prototypes per warp and round, interleaved: the chains (shuffle reduction, sqrt, IEEE
   // divisions) of one prototype are ~900 cycles long with two warps per scheduler
   constexpr int kC = 5;
@@ -160,9 +163,9 @@ __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
             const float u = v[i][s] / div;
             pf[k * dim + d] = u;
             const __nv_bfloat16 h = __float2bfloat16_rn(u);
-            const uint32_t off = operand_offset(k, d);
+            const uint32_t off = operand_offset(k, d, b_part);
             *reinterpret_cast<__nv_bfloat16*>(b_tile + off) = h;
-            *reinterpret_cast<__nv_bfloat16*>(b_tile + off + kSmBlockBytes) =
+            *reinterpret_cast<__nv_bfloat16*>(b_tile + off + b_part) =
                 __float2bfloat16_rn(u - __bfloat162float(h));
           }
         }
@@ -326,7 +329,8 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   uint8_t* b_tile = a_lo + (size_t)a.nkb * kSmBlockBytes;      // [nkb][hi | lo]
   // the tile's contribution to the sums as two int32 halves per entry; the same bytes stage
   // the image's int64 totals while the prototypes are rebuilt (the halves are zero then)
-  int* s_hi = reinterpret_cast<int*>(b_tile + (size_t)a.nkb * 2 * kSmBlockBytes);   // [K][dim]
+  const uint32_t b_part = (uint32_t)a.bn * 128;                // bytes of the hi (or lo) rows of a K block
+  int* s_hi = reinterpret_cast<int*>(b_tile + (size_t)a.nkb * 2 * b_part);   // [K][dim]
   int* s_lo = s_hi + per_img;
   long long* s_tot = reinterpret_cast<long long*>(s_hi);
   float* pf = reinterpret_cast<float*>(s_lo + per_img);        // [K][dim] fp32 prototypes
@@ -342,7 +346,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   }
   if (warp == 1) tc::tmem_alloc(&s_tmem_base, 2 * kSmBN);   // one accumulator [hh + lh | hl]
   // operand tile: rows >= K and the K padding [dim, 64 nkb) must be zeros (0 x garbage = NaN)
-  for (int i = tid; i < a.nkb * 2 * kSmBlockBytes / 16; i += kGemmThreads)
+  for (int i = tid; i < a.nkb * 2 * (int)b_part / 16; i += kGemmThreads)
     reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < per_img; i += kGemmThreads) s_hi[i] = 0, s_lo[i] = 0;
   tc::tcgen05_fence_before();
@@ -350,8 +354,10 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, kSmBN, 0, 0);
-  constexpr uint32_t idesc2x = tc::umma_idesc_bf16(BM, 2 * kSmBN, 0, 0);
+  const uint32_t idesc = a.bn == 64 ? tc::umma_idesc_bf16(BM, 64, 0, 0)
+                                    : tc::umma_idesc_bf16(BM, 128, 0, 0);
+  const uint32_t idesc2x = a.bn == 64 ? tc::umma_idesc_bf16(BM, 128, 0, 0)
+                                      : tc::umma_idesc_bf16(BM, 256, 0, 0);
   const uint32_t hi_k = tc::umma_desc_hi_sw128(1024);
   const uint32_t ah_lo = tc::umma_desc_lo(tc::smem_u32(a_hi), 16);
   const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
@@ -524,7 +530,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
             }
           }
           KMS(12);
-          KMS_SLOT_SWITCH(dim, (build_prototypes<kS>(p, s_tot, kb, pf, b_tile)));
+          KMS_SLOT_SWITCH(dim, (build_prototypes<kS>(p, s_tot, kb, pf, b_tile, b_part)));
           KMS(13);
           __syncthreads();
           for (int i = tid; i < per_img; i += kGemmThreads) s_hi[i] = 0, s_lo[i] = 0;
@@ -549,7 +555,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
               const int steps = min(4, a.ksteps - kblk * 4);
               uint32_t ah = ah_lo + kblk * (kSmBlockBytes >> 4);
               uint32_t al = al_lo + kblk * (kSmBlockBytes >> 4);
-              uint32_t bp = b_lo + kblk * (2 * kSmBlockBytes >> 4);
+              uint32_t bp = b_lo + kblk * (2 * b_part >> 4);
               for (int ks = 0; ks < steps; ++ks) {   // 16 bf16 = 32 bytes inside the swizzle atom
                 tc::umma_bf16_words(tmem_base, ah, hi_k, bp, hi_k, idesc2x, accumulate);   // hh | hl
                 tc::umma_bf16_words(tmem_base, al, hi_k, bp, hi_k, idesc, 1);              // += lh
@@ -578,7 +584,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
             uint32_t v[32], w[32];
             const uint32_t taddr = tmem_base + cb + (static_cast<uint32_t>(sp * 32) << 16);
             tc::tmem_ld_32x32(taddr, v);            // hi.hi + lo.hi
-            tc::tmem_ld_32x32(taddr + kSmBN, w);    // hi.lo
+            tc::tmem_ld_32x32(taddr + a.bn, w);     // hi.lo
             tc::tmem_ld_wait();
             const int live = kb - cb;               // columns of this chunk that exist
 #pragma unroll
@@ -715,12 +721,15 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
 
 // ------------------------------------------------------------------------- host side
 
-static bool kmeans_small_geometry(int dim, int num_clusters, int* nkb, int* prefetch, size_t* smem) {
+static bool kmeans_small_geometry(int dim, int num_clusters, int* nkb, int* bn, int* prefetch,
+                                  size_t* smem) {
   const int blocks = (dim + 63) / 64;
   if (dim < 1 || blocks > 2 || num_clusters < 1 || num_clusters > kSmBN) return false;
   if (num_clusters * dim > (1 << 15)) return false;
   const size_t tile = ((size_t)BM * dim + 4) * sizeof(float);
-  const size_t fixed = 1024 + (size_t)4 * blocks * kSmBlockBytes +            // A hi/lo, B hi/lo
+  *bn = num_clusters <= 64 ? 64 : kSmBN;
+  const size_t fixed = 1024 + (size_t)2 * blocks * kSmBlockBytes +            // A hi / lo
+                       (size_t)2 * blocks * *bn * 128 +                       // B hi / lo
                        (size_t)num_clusters * dim * (sizeof(float) + 2 * sizeof(int)) + 64;   // sums, fp32 rows
   if (fixed + tile > 220 * 1024) return false;
   *nkb = blocks;
@@ -730,17 +739,17 @@ static bool kmeans_small_geometry(int dim, int num_clusters, int* nkb, int* pref
 }
 
 bool kmeans_small_supported(int dim, int num_clusters, int batch, int64_t rows) {
-  int nkb, prefetch;
+  int nkb, bn, prefetch;
   size_t smem;
   // (offsets are cached as int32 in shared memory; an image has fewer than 2^16 tiles)
   if (batch > kSmMaxBatch || rows >= (1ll << 22) * batch || rows >= (1ll << 31)) return false;
-  return kmeans_small_geometry(dim, num_clusters, &nkb, &prefetch, &smem);
+  return kmeans_small_geometry(dim, num_clusters, &nkb, &bn, &prefetch, &smem);
 }
 
 int kmeans_small_launch(const KmeansArgs& p, int sms, cudaStream_t st) {
   KmeansSmallArgs a{};
   size_t smem = 0;
-  if (!kmeans_small_geometry(p.dim, p.num_clusters, &a.nkb, &a.prefetch, &smem)) {
+  if (!kmeans_small_geometry(p.dim, p.num_clusters, &a.nkb, &a.bn, &a.prefetch, &smem)) {
     set_error("kmeans(small): dim %d, %d clusters are not supported", p.dim, p.num_clusters);
     return SPML_E_UNSUPPORTED;
   }

@@ -308,23 +308,38 @@ struct FinishArgs {
 __global__ void head_finish_kernel(FinishArgs f, const int32_t* __restrict__ hits, float w_ann,
                                    float w_occ, float w_sim, int k, unsigned enable,
                                    float* __restrict__ out) {
+  __shared__ float s_loss[3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < 3) {
     const float w = warp == 0 ? w_ann : (warp == 1 ? w_occ : w_sim);
     float v = 0.f;
     if (enable & (1u << warp)) v = segsort_finalize_loss(f.desc[warp], f.partial[warp], f.tiles_x[warp]) * w;
-    if (lane == 0) out[warp] = v;
+    if (lane == 0) out[warp] = v, s_loss[warp] = v;
   } else if (lane == 0) {
     out[3] = (enable & 8u) ? (float)hits[0] / ((float)hits[1] * (float)k) : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // Python's sum([...]) over the enabled losses: ((0 + a) + b) + c, 0 + a being exact
+    float total = 0.f;
+    bool first = true;
+    for (int i = 0; i < 3; ++i)
+      if (enable & (1u << i)) {
+        total = first ? s_loss[i] : total + s_loss[i];
+        first = false;
+      }
+    out[4] = total;
   }
 }
 
 __global__ void scale_grads_kernel(const float* g_ann, const float* g_occ, const float* g_sim,
-                                   float w_ann, float w_occ, float w_sim, float* __restrict__ out) {
+                                   const float* g_total, float w_ann, float w_occ, float w_sim,
+                                   float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  out[0] = g_ann ? *g_ann * w_ann : 0.f;
-  out[1] = g_occ ? *g_occ * w_occ : 0.f;
-  out[2] = g_sim ? *g_sim * w_sim : 0.f;
+  const float t = g_total ? *g_total : 0.f;
+  out[0] = ((g_ann ? *g_ann : 0.f) + t) * w_ann;
+  out[1] = ((g_occ ? *g_occ : 0.f) + t) * w_occ;
+  out[2] = ((g_sim ? *g_sim : 0.f) + t) * w_sim;
 }
 
 __global__ void add_rows_kernel(const float* __restrict__ a, int64_t count, float* __restrict__ out) {
@@ -355,8 +370,6 @@ struct HeadPlan {
   float* sim_protos;      // [m, dim_sim] per-image prototypes of the img_sim embeddings
   float* sim_norms;       // [m]
   float* d_sim_protos;    // [m, dim_sim] (backward)
-  float* dp_ann;          // [m_all, dim] (backward)
-  float* dp_occ;          // [m_all, dim] (backward)
   float* stats[3];        // [n, 3] each
   float* raw;             // [4] unweighted losses
   float* gw;              // [4] weighted incoming gradients (backward)
@@ -401,8 +414,6 @@ static HeadPlan head_plan(const spml_head_args& a, void* base) {
   p.sim_protos = c.take<float>((size_t)a.m * dsim);
   p.sim_norms = c.take<float>(a.m);
   p.d_sim_protos = c.take<float>((size_t)a.m * dsim);
-  p.dp_ann = c.take<float>((size_t)m_all * a.dim);
-  p.dp_occ = c.take<float>((size_t)m_all * a.dim);
   for (int i = 0; i < 3; ++i) p.stats[i] = c.take<float>((size_t)n * 3);
   p.raw = c.take<float>(4);
   p.gw = c.take<float>(4);
@@ -818,8 +829,8 @@ int spml_head_fwd(const spml_head_args* a, void* state, size_t state_bytes, floa
 }
 
 int spml_head_bwd(const spml_head_args* a, void* state, size_t state_bytes, const float* g_ann,
-                  const float* g_occ, const float* g_sim, float* de, float* del, float* dprotos,
-                  void* stream) {
+                  const float* g_occ, const float* g_sim, const float* g_total, float* de,
+                  float* del, float* dprotos, void* stream) {
   using namespace spml;
   SPML_TRY(check_head(a, "head_bwd"));
   SPML_CHECK_ARG(state, "head_bwd: null pointer");
@@ -831,8 +842,9 @@ int spml_head_bwd(const spml_head_args* a, void* state, size_t state_bytes, cons
   cudaStream_t st = as_stream(stream);
   StreamPool* pool = nullptr;
   SPML_TRY(get_pool(&pool));
-  const bool ann = (a->enable & kAnn) && g_ann, occ = (a->enable & kOcc) && g_occ;
-  const bool sim = (a->enable & kSim) && g_sim;
+  const bool ann = (a->enable & kAnn) && (g_ann || g_total);
+  const bool occ = (a->enable & kOcc) && (g_occ || g_total);
+  const bool sim = (a->enable & kSim) && (g_sim || g_total);
   const int64_t n = a->n;
   const int dsim = head_dim_sim(*a);
   float* d_sim_emb = a->img_sim_on_plain ? de : del;
@@ -846,19 +858,25 @@ int spml_head_bwd(const spml_head_args* a, void* state, size_t state_bytes, cons
   if (dprotos && !(ann || occ))
     SPML_CUDA(cudaMemsetAsync(dprotos, 0, (size_t)a->m * a->dim * 4, st));
   scale_grads_kernel<<<1, 32, 0, st>>>(ann ? g_ann : nullptr, occ ? g_occ : nullptr,
-                                       sim ? g_sim : nullptr, a->weight_ann, a->weight_occ,
-                                       a->weight_sim, p.gw);
+                                       sim ? g_sim : nullptr, g_total, a->weight_ann,
+                                       a->weight_occ, a->weight_sim, p.gw);
   SPML_LAUNCH_CHECK("scale_grads_kernel");
   for (int i = 0; i < 3; ++i) p.desc[i].reserved |= 4;   // operands prepared by the forward
 
   SPML_TRY(fork_streams(*pool, st, kSideStreams));
-  // d(prototypes) of sem_occ / sem_ann on side streams 1 / 2 (separate buffers)
+  // d(prototypes) of sem_occ / sem_ann on side streams 1 / 2: only the current step's
+  // prototypes carry a gradient (the memory bank behind them is detached); the per-chunk
+  // partial sums of both problems stay in their workspaces and are added once after the join
+  const float *part_occ = nullptr, *part_ann = nullptr;
+  int chunks_occ = 0, chunks_ann = 0;
   if (occ && dprotos)
-    SPML_TRY(spml_segsort_bwd(&p.desc[1], p.stats[1], p.gw + 1, 0.f, nullptr, a->dim, p.dp_occ,
-                              p.seg_ws[1], p.seg_ws_bytes[1], pool->side[1]));
+    SPML_TRY(segsort_bwd_impl(&p.desc[1], p.stats[1], p.gw + 1, 0.f, nullptr, a->dim, nullptr,
+                              a->m, &part_occ, &chunks_occ, p.seg_ws[1], p.seg_ws_bytes[1],
+                              pool->side[1]));
   if (ann && dprotos)
-    SPML_TRY(spml_segsort_bwd(&p.desc[0], p.stats[0], p.gw + 0, 0.f, nullptr, a->dim, p.dp_ann,
-                              p.seg_ws[0], p.seg_ws_bytes[0], pool->side[2]));
+    SPML_TRY(segsort_bwd_impl(&p.desc[0], p.stats[0], p.gw + 0, 0.f, nullptr, a->dim, nullptr,
+                              a->m, &part_ann, &chunks_ann, p.seg_ws[0], p.seg_ws_bytes[0],
+                              pool->side[2]));
   // img_sim: d(embedding) and d(per-image prototypes) -> segment-prototype backward
   if (sim && !a->img_sim_on_plain) {
     cudaStream_t s0 = pool->side[0];
@@ -882,16 +900,9 @@ int spml_head_bwd(const spml_head_args* a, void* state, size_t state_bytes, cons
                                          nullptr, dsim, a->m, a->eps, 1.f, de, stream));
   }
   for (int i = 0; i < kSideStreams; ++i) SPML_TRY(join_stream(*pool, i, st));
-  if (dprotos && (ann || occ)) {
-    // only the current step's prototypes carry a gradient (the memory bank is detached)
-    const int64_t count = a->m * a->dim;
-    const float* first = occ ? p.dp_occ : p.dp_ann;
-    SPML_CUDA(cudaMemcpyAsync(dprotos, first, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));
-    if (occ && ann) {
-      add_rows_kernel<<<blocks_of(count), 256, 0, st>>>(p.dp_ann, count, dprotos);
-      SPML_LAUNCH_CHECK("add_rows_kernel");
-    }
-  }
+  if (dprotos && (ann || occ))
+    SPML_TRY(segsort_reduce_two(part_occ, chunks_occ, part_ann, chunks_ann, a->m * a->dim, dprotos,
+                                st));
   return SPML_OK;
 }
 

@@ -325,7 +325,7 @@ template <int ND>
 __global__ void __launch_bounds__(kGemmThreads)
 segsort_bwd_proto_kernel(spml_segsort_desc d, int dpad, const float* __restrict__ stats,
                          const float* __restrict__ grad_loss, const float* __restrict__ grad_rows,
-                         float* __restrict__ partial /* [chunks][m][dim] */) {
+                         int64_t proto_rows, float* __restrict__ partial /* [chunks][proto_rows][dim] */) {
   extern __shared__ __align__(16) float smem[];
   const int ldp = dpad + 4;
   float* At = smem;                        // [dpad][LDA]; reused as Gs[BM][LDB] after GEMM 1
@@ -342,7 +342,7 @@ segsort_bwd_proto_kernel(spml_segsort_desc d, int dpad, const float* __restrict_
   TileInfo t;
   group_range(d, g, t);
   const int c0 = t.c_begin + blockIdx.x * BN;
-  if (c0 >= t.c_end) return;
+  if (c0 >= t.c_end || c0 >= proto_rows) return;
   const int64_t tiles = (t.r_end - t.r_begin + BM - 1) / BM;
   const int64_t per = (tiles + chunks - 1) / chunks;
   const int64_t tile_lo = chunk * per, tile_hi = min(tiles, tile_lo + per);
@@ -403,11 +403,11 @@ segsort_bwd_proto_kernel(spml_segsort_desc d, int dpad, const float* __restrict_
       }
     }
   }
-  float* out = partial + (size_t)chunk * d.m * d.dim;
+  float* out = partial + (size_t)chunk * proto_rows * d.dim;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty * 4 + i;
-    if (c >= t.c_end) continue;
+    if (c >= t.c_end || c >= proto_rows) continue;
 #pragma unroll
     for (int n = 0; n < ND; ++n)
 #pragma unroll
@@ -416,15 +416,6 @@ segsort_bwd_proto_kernel(spml_segsort_desc d, int dpad, const float* __restrict_
         if (q < d.dim) out[(size_t)c * d.dim + q] = pacc[i][n * 4 + j];
       }
   }
-}
-
-__global__ void reduce_chunks_kernel(const float* __restrict__ partial, int chunks, int64_t count,
-                                     float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float v = 0.f;
-  for (int c = 0; c < chunks; ++c) v += partial[(size_t)c * count + i];
-  out[i] = v;
 }
 
 // ------------------------------------------------------------------------- host side
@@ -528,6 +519,159 @@ int segsort_fwd_partial(const spml_segsort_desc* d, float* stats, float* nll, vo
 
 }  // namespace spml
 
+namespace spml {
+
+__global__ void reduce_chunks_kernel(const float* __restrict__ partial, int chunks, int64_t count,
+                                     float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = 0.f;
+  for (int c = 0; c < chunks; ++c) v += partial[(size_t)c * count + i];
+  out[i] = v;
+}
+
+// out = sum of the chunks of up to two partial buffers (the stage-group backward adds the
+// prototype gradients of sem_occ and sem_ann in one pass)
+__global__ void reduce_two_kernel(const float* __restrict__ pa, int ca,
+                                  const float* __restrict__ pb, int cb, int64_t count,
+                                  float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = 0.f;
+  for (int c = 0; c < ca; ++c) v += pa[(size_t)c * count + i];
+  for (int c = 0; c < cb; ++c) v += pb[(size_t)c * count + i];
+  out[i] = v;
+}
+
+int segsort_reduce_two(const float* pa, int ca, const float* pb, int cb, int64_t count, float* out,
+                       cudaStream_t st) {
+  if (count <= 0) return SPML_OK;
+  reduce_two_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(pa, ca, pb, cb, count, out);
+  SPML_LAUNCH_CHECK("reduce_two_kernel");
+  return SPML_OK;
+}
+
+// The backward behind spml_segsort_bwd.  `proto_rows` <= m limits d(prototypes) to the first
+// proto_rows prototypes (the memory bank behind them is detached): dprotos is
+// [proto_rows, dim].  With `partial_out` the per-chunk partial sums
+// [*chunks_out][proto_rows][dim] are left in the workspace instead of being reduced into
+// `dprotos` (then unused); *chunks_out = 0 when there is nothing to add.
+int segsort_bwd_impl(const spml_segsort_desc* d, const float* stats, const float* grad_loss,
+                     float beta, float* demb, int64_t ld_demb, float* dprotos, int64_t proto_rows,
+                     const float** partial_out, int* chunks_out, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+  int rc = check_desc(d, "segsort_bwd");
+  if (rc != SPML_OK) return rc;
+  const bool want_protos = dprotos || partial_out;
+  SPML_CHECK_ARG(grad_loss && (stats || d->n_rows == 0) && (demb || want_protos),
+                 "segsort_bwd: null pointer");
+  SPML_CHECK_ARG(!demb || ld_demb >= d->dim, "segsort_bwd: bad ld_demb");
+  SPML_CHECK_ARG(!partial_out || chunks_out, "segsort_bwd: null pointer");
+  proto_rows = std::max<int64_t>(0, std::min<int64_t>(proto_rows, d->m));
+  const int dpad = pad4(d->dim);
+  const int ldp = dpad + 4;
+  const int nd = (dpad + 63) / 64;
+  const int tiles_x = tiles_x_of(*d);
+  const int64_t count = proto_rows * d->dim;
+  if (partial_out) {
+    *partial_out = nullptr;
+    *chunks_out = 0;
+  }
+  if (d->n_rows == 0 || d->m == 0 || d->max_rows_per_group == 0) {
+    if (dprotos && !partial_out && count > 0)
+      SPML_CUDA(cudaMemsetAsync(dprotos, 0, (size_t)count * sizeof(float), st));
+    return SPML_OK;
+  }
+  const bool protos_now = want_protos && proto_rows > 0;
+
+  if (use_tc_path(*d)) {
+    if (!workspace || workspace_bytes < spml_segsort_workspace_bytes(d)) {
+      set_error("segsort_bwd: workspace %zu < %zu bytes", workspace_bytes,
+                spml_segsort_workspace_bytes(d));
+      return SPML_E_WORKSPACE;
+    }
+    const TcPlan plan = segsort_tc_plan(*d, workspace);
+    const int chunks = segsort_tc_proto_chunks(*d, proto_rows);
+    float* partial = nullptr;
+    if (protos_now) {
+      partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + plan.bytes);
+      SPML_CUDA(cudaMemsetAsync(partial, 0, (size_t)chunks * count * sizeof(float), st));
+    }
+    rc = segsort_bwd_tc(*d, plan, stats, grad_loss, beta, demb, ld_demb, partial, chunks,
+                        proto_rows, (d->reserved & 4) != 0, st);
+    if (rc != SPML_OK) return rc;
+    if (protos_now) {
+      if (partial_out) {
+        *partial_out = partial;
+        *chunks_out = chunks;
+      } else {
+        reduce_chunks_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, chunks,
+                                                                             count, dprotos);
+        SPML_LAUNCH_CHECK("reduce_chunks_kernel");
+      }
+    }
+    return SPML_OK;
+  }
+
+  if (demb) {
+    const size_t smem = ((size_t)dpad * (LDA + LDB) + (size_t)BN * ldp + (size_t)BN * LDA) * sizeof(float);
+    dim3 grid((unsigned)tiles_x, (unsigned)d->num_groups);
+#define SPML_LAUNCH_EMB(NDV)                                                                   \
+  do {                                                                                         \
+    rc = set_smem(segsort_bwd_emb_kernel<NDV>, smem, "segsort_bwd(emb)");                       \
+    if (rc != SPML_OK) return rc;                                                              \
+    segsort_bwd_emb_kernel<NDV><<<grid, kGemmThreads, smem, st>>>(*d, dpad, stats, grad_loss,   \
+                                                                  nullptr, beta, demb, ld_demb); \
+  } while (0)
+    if (nd == 1) SPML_LAUNCH_EMB(1); else if (nd == 2) SPML_LAUNCH_EMB(2); else SPML_LAUNCH_EMB(3);
+#undef SPML_LAUNCH_EMB
+    SPML_LAUNCH_CHECK("segsort_bwd_emb_kernel");
+  }
+  if (protos_now) {
+    // the workspace holds proto_chunks_of(d) x m x dim floats: the rows are split finer when
+    // fewer prototypes need a gradient, as long as the partials still fit
+    int chunks = proto_chunks_of(*d);
+    if (proto_rows < d->m) {
+      const int64_t col_tiles = std::max<int64_t>(1, ceil_div(proto_rows, BN));
+      const int64_t want =
+          std::min<int64_t>(ceil_div(2 * 148, col_tiles * d->num_groups), tiles_x);
+      chunks = (int)std::max<int64_t>(
+          1, std::min<int64_t>(want, (int64_t)chunks * d->m / proto_rows));
+    }
+    const size_t need = (size_t)chunks * count * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("segsort_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+      return SPML_E_WORKSPACE;
+    }
+    float* partial = reinterpret_cast<float*>(workspace);
+    SPML_CUDA(cudaMemsetAsync(partial, 0, need, st));
+    const size_t smem =
+        (proto_at_floats(dpad) + (size_t)dpad * LDB + (size_t)BM * ldp) * sizeof(float);
+    dim3 grid((unsigned)ceil_div(proto_rows, BN), (unsigned)d->num_groups, (unsigned)chunks);
+#define SPML_LAUNCH_PROTO(NDV)                                                                  \
+  do {                                                                                          \
+    rc = set_smem(segsort_bwd_proto_kernel<NDV>, smem, "segsort_bwd(protos)");                  \
+    if (rc != SPML_OK) return rc;                                                               \
+    segsort_bwd_proto_kernel<NDV><<<grid, kGemmThreads, smem, st>>>(                            \
+        *d, dpad, stats, grad_loss, nullptr, proto_rows, partial);                              \
+  } while (0)
+    if (nd == 1) SPML_LAUNCH_PROTO(1); else if (nd == 2) SPML_LAUNCH_PROTO(2); else SPML_LAUNCH_PROTO(3);
+#undef SPML_LAUNCH_PROTO
+    SPML_LAUNCH_CHECK("segsort_bwd_proto_kernel");
+    if (partial_out) {
+      *partial_out = partial;
+      *chunks_out = chunks;
+    } else {
+      reduce_chunks_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, chunks, count,
+                                                                           dprotos);
+      SPML_LAUNCH_CHECK("reduce_chunks_kernel");
+    }
+  }
+  return SPML_OK;
+}
+
+}  // namespace spml
+
 extern "C" {
 
 size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
@@ -537,7 +681,7 @@ size_t spml_segsort_workspace_bytes(const spml_segsort_desc* d) {
   size_t need = 16 + (fwd > bwd ? fwd : bwd);
   if (spml::segsort_tc_supported(*d)) {
     const size_t tc = spml::segsort_tc_plan(*d, nullptr).bytes +
-                      (size_t)spml::segsort_tc_proto_chunks(*d) * d->m * d->dim * sizeof(float);
+                      (size_t)spml::segsort_tc_proto_chunks(*d, d->m) * d->m * d->dim * sizeof(float);
     need = std::max(need, tc);
   }
   return need;
@@ -560,89 +704,19 @@ int spml_segsort_fwd(const spml_segsort_desc* d, float* stats, float* nll, float
 int spml_segsort_bwd(const spml_segsort_desc* d, const float* stats, const float* grad_loss,
                      float beta, float* demb, int64_t ld_demb, float* dprotos, void* workspace,
                      size_t workspace_bytes, void* stream) {
-  using namespace spml;
-  int rc = check_desc(d, "segsort_bwd");
-  if (rc != SPML_OK) return rc;
-  SPML_CHECK_ARG(grad_loss && (stats || d->n_rows == 0) && (demb || dprotos),
-                 "segsort_bwd: null pointer");
-  SPML_CHECK_ARG(!demb || ld_demb >= d->dim, "segsort_bwd: bad ld_demb");
-  cudaStream_t st = as_stream(stream);
-  const int dpad = pad4(d->dim);
-  const int ldp = dpad + 4;
-  const int nd = (dpad + 63) / 64;
-  const int tiles_x = tiles_x_of(*d);
-  if (dprotos && d->m > 0)
-    SPML_CUDA(cudaMemsetAsync(dprotos, 0, (size_t)d->m * d->dim * sizeof(float), st));
-  if (d->n_rows == 0 || d->m == 0 || d->max_rows_per_group == 0) return SPML_OK;
+  return spml::segsort_bwd_impl(d, stats, grad_loss, beta, demb, ld_demb, dprotos,
+                                d ? d->m : 0, nullptr, nullptr, workspace, workspace_bytes,
+                                spml::as_stream(stream));
+}
 
-  if (use_tc_path(*d)) {
-    if (!workspace || workspace_bytes < spml_segsort_workspace_bytes(d)) {
-      set_error("segsort_bwd: workspace %zu < %zu bytes", workspace_bytes,
-                spml_segsort_workspace_bytes(d));
-      return SPML_E_WORKSPACE;
-    }
-    const TcPlan plan = segsort_tc_plan(*d, workspace);
-    const int chunks = segsort_tc_proto_chunks(*d);
-    float* partial = nullptr;
-    const size_t partial_bytes = (size_t)chunks * d->m * d->dim * sizeof(float);
-    if (dprotos) {
-      partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + plan.bytes);
-      SPML_CUDA(cudaMemsetAsync(partial, 0, partial_bytes, st));
-    }
-    rc = segsort_bwd_tc(*d, plan, stats, grad_loss, beta, demb, ld_demb, partial, chunks,
-                        (d->reserved & 4) != 0, st);
-    if (rc != SPML_OK) return rc;
-    if (dprotos) {
-      const int64_t count = d->m * d->dim;
-      reduce_chunks_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, chunks, count,
-                                                                           dprotos);
-      SPML_LAUNCH_CHECK("reduce_chunks_kernel");
-    }
-    return SPML_OK;
-  }
-
-  if (demb) {
-    const size_t smem = ((size_t)dpad * (LDA + LDB) + (size_t)BN * ldp + (size_t)BN * LDA) * sizeof(float);
-    dim3 grid((unsigned)tiles_x, (unsigned)d->num_groups);
-#define SPML_LAUNCH_EMB(NDV)                                                                   \
-  do {                                                                                         \
-    rc = set_smem(segsort_bwd_emb_kernel<NDV>, smem, "segsort_bwd(emb)");                       \
-    if (rc != SPML_OK) return rc;                                                              \
-    segsort_bwd_emb_kernel<NDV><<<grid, kGemmThreads, smem, st>>>(*d, dpad, stats, grad_loss,   \
-                                                                  nullptr, beta, demb, ld_demb); \
-  } while (0)
-    if (nd == 1) SPML_LAUNCH_EMB(1); else if (nd == 2) SPML_LAUNCH_EMB(2); else SPML_LAUNCH_EMB(3);
-#undef SPML_LAUNCH_EMB
-    SPML_LAUNCH_CHECK("segsort_bwd_emb_kernel");
-  }
-  if (dprotos) {
-    const int chunks = proto_chunks_of(*d);
-    const size_t need = (size_t)chunks * d->m * d->dim * sizeof(float);
-    if (!workspace || workspace_bytes < need) {
-      set_error("segsort_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
-      return SPML_E_WORKSPACE;
-    }
-    float* partial = reinterpret_cast<float*>(workspace);
-    SPML_CUDA(cudaMemsetAsync(partial, 0, need, st));
-    const size_t smem =
-        (proto_at_floats(dpad) + (size_t)dpad * LDB + (size_t)BM * ldp) * sizeof(float);
-    dim3 grid((unsigned)ceil_div(d->m, BN), (unsigned)d->num_groups, (unsigned)chunks);
-#define SPML_LAUNCH_PROTO(NDV)                                                                  \
-  do {                                                                                          \
-    rc = set_smem(segsort_bwd_proto_kernel<NDV>, smem, "segsort_bwd(protos)");                  \
-    if (rc != SPML_OK) return rc;                                                               \
-    segsort_bwd_proto_kernel<NDV><<<grid, kGemmThreads, smem, st>>>(*d, dpad, stats, grad_loss, \
-                                                                    nullptr, partial);          \
-  } while (0)
-    if (nd == 1) SPML_LAUNCH_PROTO(1); else if (nd == 2) SPML_LAUNCH_PROTO(2); else SPML_LAUNCH_PROTO(3);
-#undef SPML_LAUNCH_PROTO
-    SPML_LAUNCH_CHECK("segsort_bwd_proto_kernel");
-    const int64_t count = d->m * d->dim;
-    reduce_chunks_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, chunks, count,
-                                                                         dprotos);
-    SPML_LAUNCH_CHECK("reduce_chunks_kernel");
-  }
-  return SPML_OK;
+int spml_segsort_bwd_rows(const spml_segsort_desc* d, const float* stats, const float* grad_loss,
+                          float beta, float* demb, int64_t ld_demb, float* dprotos,
+                          int64_t dprotos_rows, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  SPML_CHECK_ARG(!d || (dprotos_rows >= 0 && dprotos_rows <= d->m), "segsort_bwd: bad dprotos_rows");
+  return spml::segsort_bwd_impl(d, stats, grad_loss, beta, demb, ld_demb, dprotos, dprotos_rows,
+                                nullptr, nullptr, workspace, workspace_bytes,
+                                spml::as_stream(stream));
 }
 
 }  // extern "C"

@@ -512,6 +512,8 @@ struct TcBwdArgs {
   int n2;                     // GEMM 2 N: dim rounded up to 16
   int tmem_cols;
   int stacked;                // nkb == 1: hi/lo streamed tiles read as one operand (2 MMAs per K step)
+  int64_t proto_rows;         // prototype-owner kernel: only prototypes [0, proto_rows) get a
+                              // gradient; the partials are [chunks][proto_rows][dim]
 };
 
 // Per-pixel gradient weights.  G_ij = S_ij * w(match_ij, own_ij) with
@@ -600,13 +602,15 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
     s_hi = c_end;
   } else {
     o0 = c_begin + (int64_t)blockIdx.x * kBwdBM;
-    o_end = c_end;
+    o_end = a.col_src ? (int64_t)c_end : min((int64_t)c_end, a.proto_rows);
     const int64_t steps = (r_end - r_begin + kBwdBN - 1) / kBwdBN;
     const int64_t per = (steps + gridDim.z - 1) / gridDim.z;
     s_lo = r_begin + (int64_t)blockIdx.z * per * kBwdBN;
     s_hi = min(r_end, s_lo + per * kBwdBN);
   }
   if (o0 >= o_end) return;
+  // compacted columns keep their order: a tile that starts past the limit has nothing to do
+  if (kProtoOwner && a.col_src && a.col_src[o0] >= a.proto_rows) return;
   const int owned = (int)min((int64_t)kBwdBM, o_end - o0);
   if (s_lo >= s_hi) {
     // nothing streams past this tile: dP partials are pre-zeroed, dE rows are written here
@@ -973,7 +977,8 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
         out_row = a.out + orig * a.ld_out;
       } else {
         const int64_t orig = a.col_src ? (int64_t)a.col_src[orow] : orow;
-        out_row = a.out + ((size_t)blockIdx.z * d.m + orig) * d.dim;
+        out_row = a.out + ((size_t)blockIdx.z * a.proto_rows + orig) * d.dim;
+        if (orig >= a.proto_rows) out_row = nullptr;
       }
     }
     const int nchunks = (a.n2 + 31) / 32;
@@ -990,7 +995,7 @@ segsort_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_ah,
       } else {
         tc::tmem_ld_wait();
       }
-      if (row_ok) {
+      if (out_row) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const int col = ch * 32 + q;
@@ -1127,8 +1132,8 @@ int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, fl
 __device__ long long g_tc_trace[64 * 16];
 #endif
 
-int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
-  const int64_t col_tiles = std::max<int64_t>(1, ceil_div(d.m, kBwdBM));
+static int proto_chunks_for(const spml_segsort_desc& d, int64_t m) {
+  const int64_t col_tiles = std::max<int64_t>(1, ceil_div(m, kBwdBM));
   const int64_t steps = std::max<int64_t>(1, ceil_div(d.max_rows_per_group, kBwdBN));
   // with per-group column ranges (img_sim) a group only owns ~1 / num_groups of the column
   // tiles: the others exit at once, so they must not count as work when the rows are split
@@ -1141,9 +1146,20 @@ int segsort_tc_proto_chunks(const spml_segsort_desc& d) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(chunks, steps));
 }
 
+// Row chunks of the prototype-owner kernel.  The workspace is sized for proto_rows = m; with
+// fewer gradient rows there are fewer column tiles, so the rows are split finer as long as
+// the [chunks][proto_rows][dim] partials still fit into that space.
+int segsort_tc_proto_chunks(const spml_segsort_desc& d, int64_t proto_rows) {
+  const int full = proto_chunks_for(d, d.m);
+  if (proto_rows >= d.m || proto_rows <= 0) return full;
+  const int64_t fits = (int64_t)full * d.m / proto_rows;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(proto_chunks_for(d, proto_rows), fits));
+}
+
 int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
                    const float* grad_loss, float beta, float* demb, int64_t ld_demb,
-                   float* proto_partial, int chunks, bool prepared, cudaStream_t st) {
+                   float* proto_partial, int chunks, int64_t proto_rows, bool prepared,
+                   cudaStream_t st) {
   int rc = prepared ? SPML_OK : segsort_tc_prepare(d, p, st);
   if (rc != SPML_OK) return rc;
   const uint64_t pitch = (uint64_t)p.dp * 2;
@@ -1170,6 +1186,7 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     stack_mode = e ? atoi(e) : 1;
   }
   a.stacked = stack_mode && p.nkb == 1;
+  a.proto_rows = proto_rows;
   // TMEM columns: S buffers | d(owner)
   const int s_cols = a.stacked ? 4 * kBwdBN : 2 * kBwdBN;
   const int d_cols = a.stacked ? 64 + a.n2 : a.n2;
@@ -1227,7 +1244,10 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
     if (getenv("SPML_B200_TRACE_PROTO"))
       SPML_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.trace), g_tc_trace));
 #endif
-    dim3 grid((unsigned)ceil_div(d.m, kBwdBM), (unsigned)d.num_groups, (unsigned)chunks);
+    // compacted columns: the live tiles are only known on the device (dead ones exit at once)
+    const int64_t owner_cols = d.proto_valid ? d.m : std::min<int64_t>(d.m, proto_rows);
+    dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(owner_cols, kBwdBM)),
+              (unsigned)d.num_groups, (unsigned)chunks);
     if (d.mode == SPML_MODE_TAGS) {
       SPML_CUDA(cudaFuncSetAttribute(segsort_bwd_tc_kernel<true, SPML_MODE_TAGS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

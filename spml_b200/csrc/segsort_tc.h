@@ -42,10 +42,12 @@ int segsort_tc_prepare(const spml_segsort_desc& d, const TcPlan& p, cudaStream_t
 int segsort_fwd_tc(const spml_segsort_desc& d, const TcPlan& p, float* stats, float* nll,
                    cudaStream_t st);
 // backward: demb (nullable) and dprotos (nullable); `proto_partial` is the zeroed
-// [chunks][m][dim] buffer the prototype-gradient CTAs write, reduced by the caller.
-int segsort_tc_proto_chunks(const spml_segsort_desc& d);
+// [chunks][proto_rows][dim] buffer the prototype-gradient CTAs write (only prototypes
+// [0, proto_rows) get a gradient), reduced by the caller.
+int segsort_tc_proto_chunks(const spml_segsort_desc& d, int64_t proto_rows);
 int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* stats,
                    const float* grad_loss, float beta, float* demb, int64_t ld_demb,
-                   float* proto_partial, int chunks, bool prepared, cudaStream_t st);
+                   float* proto_partial, int chunks, int64_t proto_rows, bool prepared,
+                   cudaStream_t st);
 
 }  // namespace spml

@@ -334,19 +334,20 @@ struct HeadCall {
     a.status = status.data_ptr<int32_t>();
     const size_t bytes = spml_head_workspace_bytes(&a);
     state = workspace(bytes, e);
-    Tensor out = at::empty({4}, e.options());
+    Tensor out = at::empty({5}, e.options());
     check(spml_head_fwd(&a, state.data_ptr(), bytes, out.data_ptr<float>(), stream_of(e)),
           "spml_head_fwd");
     return out;
   }
 
   std::vector<Tensor> backward(const OptTensor& g_ann, const OptTensor& g_occ,
-                               const OptTensor& g_sim, bool need_protos) {
+                               const OptTensor& g_sim, const OptTensor& g_total,
+                               bool need_protos) {
     c10::cuda::CUDAGuard guard(e.device());
-    Tensor g[3];
-    const OptTensor* in[3] = {&g_ann, &g_occ, &g_sim};
-    const float* gp[3] = {nullptr, nullptr, nullptr};
-    for (int i = 0; i < 3; ++i)
+    Tensor g[4];
+    const OptTensor* in[4] = {&g_ann, &g_occ, &g_sim, &g_total};
+    const float* gp[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i)
       if (in[i]->has_value() && (*in[i])->defined()) {
         g[i] = (*in[i])->scalar_type() == at::kFloat ? **in[i] : (*in[i])->to(at::kFloat);
         gp[i] = g[i].data_ptr<float>();
@@ -355,7 +356,7 @@ struct HeadCall {
     Tensor de = at::empty_like(e), del, dprotos;
     if (el.defined() && sim_on_el) del = at::empty_like(el);
     if (need_protos) dprotos = at::empty_like(protos);
-    check(spml_head_bwd(&a, state.data_ptr(), (size_t)state.numel(), gp[0], gp[1], gp[2],
+    check(spml_head_bwd(&a, state.data_ptr(), (size_t)state.numel(), gp[0], gp[1], gp[2], gp[3],
                         de.data_ptr<float>(), del.defined() ? del.data_ptr<float>() : nullptr,
                         dprotos.defined() ? dprotos.data_ptr<float>() : nullptr, stream_of(e)),
           "spml_head_bwd");

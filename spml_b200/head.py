@@ -123,9 +123,15 @@ class ContrastiveHead(nn.Module):
       targets['prototype_semantic_tag'] = torch.index_select(semantic_tag, 0, pbid[0])
     targets.update(self.memory_banks)                                  # train.py:204-208
     out = self.predictor(datas, targets)
-    losses = [out[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss')
-              if out.get(k, None) is not None]
-    out['loss'] = sum(losses)                                          # train.py:213-219
+    total = getattr(self.predictor, 'last_loss_total', None)
+    if total is not None:
+      # the head kernel already added the losses it produced (same order, same fp32 adds)
+      self.predictor.last_loss_total = None
+      out['loss'] = total
+    else:
+      losses = [out[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss')
+                if out.get(k, None) is not None]
+      out['loss'] = sum(losses)                                        # train.py:213-219
     out['datas'], out['targets'] = datas, targets
     self._last_targets, self._last_batch = targets, embedding.shape[0]
     return out
@@ -147,5 +153,6 @@ class ContrastiveHead(nn.Module):
     key = 'memory_prototype_batch_index'
     if key in self.memory_banks:
       stride = self._last_batch * num_replicas
-      self.memory_banks[key] = [t + stride for t in self.memory_banks[key]]
+      # one multi-tensor launch for the whole list
+      self.memory_banks[key] = list(torch._foreach_add(self.memory_banks[key], stride))
     self._last_targets = None

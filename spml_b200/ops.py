@@ -275,7 +275,8 @@ class SegsortProblem:
 
   def __init__(self, pix_code, seg, proto_code, kappa, mode, reduction=_lib.REDUCE_MEAN,
                row_index=None, group_off=None, col_off=None, num_groups=1, n_rows=None,
-               max_rows_per_group=None, proto_valid=None, path='auto', name=''):
+               max_rows_per_group=None, proto_valid=None, path='auto', name='',
+               proto_grad_rows=None):
     self.pix_code = _i64c(pix_code, 'segsort(pixel labels)').view(-1)
     self.seg = _i64c(seg, 'segsort(instance labels)').view(-1)
     self.proto_code = _i64c(proto_code, 'segsort(prototype labels)').view(-1)
@@ -287,6 +288,8 @@ class SegsortProblem:
                                else self.n_rows)
     self.proto_valid = proto_valid
     self.name = name      # label of this problem in bench.py's per-call profile
+    # only the first `proto_grad_rows` prototypes need a gradient (the rest: a detached bank)
+    self.proto_grad_rows = None if proto_grad_rows is None else int(proto_grad_rows)
     # 'fp32' / 'tc' pin the CUDA-core / tcgen05 kernels (tests compare the two)
     self.path_bits = {'auto': 0, 'fp32': 1, 'tc': 2}[path]
     if proto_valid is not None and proto_valid.dtype != torch.uint8:
@@ -347,14 +350,19 @@ class SegsortLossFn(torch.autograd.Function):
       # rows outside the problem (row_index subsets) must read as zero
       demb = (torch.zeros_like(emb) if problem.row_index is not None or
               problem.group_off is not None else torch.empty_like(emb))
+    rows = protos.shape[0]
     if need_p:
-      dprotos = torch.empty_like(protos)
+      if problem.proto_grad_rows is not None and problem.proto_grad_rows < rows:
+        rows = problem.proto_grad_rows
+        dprotos = torch.zeros_like(protos)       # the rows behind stay zero
+      else:
+        dprotos = torch.empty_like(protos)
     if need_e or need_p:
       ws = ctx.workspace
       d.reserved |= 4
       _lib.set_profile_tag(':' + problem.name if problem.name else '')
-      call('spml_segsort_bwd', ctypes.byref(d), ptr(stats), ptr(grad_loss), 0.0, ptr(demb),
-           emb.shape[1], ptr(dprotos), ptr(ws), ws.numel(), stream_of(emb))
+      call('spml_segsort_bwd_rows', ctypes.byref(d), ptr(stats), ptr(grad_loss), 0.0, ptr(demb),
+           emb.shape[1], ptr(dprotos), rows, ptr(ws), ws.numel(), stream_of(emb))
       _lib.set_profile_tag('')
     return demb, dprotos, None
 
@@ -776,8 +784,9 @@ class HeadSpec:
 
 class HeadLossFn(torch.autograd.Function):
   """Everything of Segsort*.losses() but the conv classifier, forward and backward, as one
-  library call each.  Returns four 0-dim tensors: weighted sem_ann, sem_occ, img_sim and the
-  top-5 accuracy (entries of disabled losses are 0)."""
+  library call each.  Returns five 0-dim tensors: weighted sem_ann, sem_occ, img_sim, the
+  top-5 accuracy (entries of disabled losses are 0) and the sum of the enabled losses
+  (what train.py:213-219 adds up: `sum(losses)`, same order, same fp32 additions)."""
 
   @staticmethod
   def forward(ctx, e, el, protos, spec):
@@ -785,9 +794,9 @@ class HeadLossFn(torch.autograd.Function):
       out = spec.call.forward(e, el, protos, status_word(e.device))
       ctx.spec = spec
       ctx.set_materialize_grads(False)
-      sem_ann, sem_occ, img_sim, acc = out.unbind(0)
+      sem_ann, sem_occ, img_sim, acc, total = out.unbind(0)
       ctx.mark_non_differentiable(acc)
-      return sem_ann, sem_occ, img_sim, acc
+      return sem_ann, sem_occ, img_sim, acc, total
     e = _f32c(e, 'cluster_embedding')
     protos = _f32c(protos, 'prototype')
     a = spec.args
@@ -801,29 +810,29 @@ class HeadLossFn(torch.autograd.Function):
       raise ValueError('embeddings / prototypes disagree with their label vectors')
     a.status = status_word(dev).data_ptr()
     state = _workspace(_lib.load().spml_head_workspace_bytes(ctypes.byref(a)), dev)
-    out = torch.empty(4, dtype=torch.float32, device=dev)
+    out = torch.empty(5, dtype=torch.float32, device=dev)
     call('spml_head_fwd', ctypes.byref(a), state.data_ptr(), state.numel(), out.data_ptr(),
          stream_of(e))
     ctx.spec, ctx.state = spec, state
     ctx.save_for_backward(e, el, protos)
     ctx.set_materialize_grads(False)
-    sem_ann, sem_occ, img_sim, acc = out.unbind(0)
+    sem_ann, sem_occ, img_sim, acc, total = out.unbind(0)
     ctx.mark_non_differentiable(acc)
-    return sem_ann, sem_occ, img_sim, acc
+    return sem_ann, sem_occ, img_sim, acc, total
 
   @staticmethod
-  def backward(ctx, g_ann, g_occ, g_sim, _g_acc):
+  def backward(ctx, g_ann, g_occ, g_sim, _g_acc, g_total):
     if ctx.spec.call is not None:
-      if g_ann is None and g_occ is None and g_sim is None:
+      if g_ann is None and g_occ is None and g_sim is None and g_total is None:
         return None, None, None, None
       need_e, need_el, need_p = ctx.needs_input_grad[:3]
-      de, del_, dprotos = ctx.spec.call.backward(g_ann, g_occ, g_sim, bool(need_p))
+      de, del_, dprotos = ctx.spec.call.backward(g_ann, g_occ, g_sim, g_total, bool(need_p))
       return (de if need_e else None), (del_ if need_el else None), dprotos, None
     e, el, protos = ctx.saved_tensors
     spec, state = ctx.spec, ctx.state
     a = spec.args
     gs = [None if g is None else (g if g.dtype == torch.float32 else g.float())
-          for g in (g_ann, g_occ, g_sim)]
+          for g in (g_ann, g_occ, g_sim, g_total)]
     if all(g is None for g in gs):
       return None, None, None, None
     need_e, need_el, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -832,7 +841,7 @@ class HeadLossFn(torch.autograd.Function):
     del_ = torch.empty_like(el) if (el is not None and sim_on_el) else None
     dprotos = torch.empty_like(protos) if need_p else None
     call('spml_head_bwd', ctypes.byref(a), ptr(state), state.numel(), ptr(gs[0]), ptr(gs[1]),
-         ptr(gs[2]),
+         ptr(gs[2]), ptr(gs[3]),
          ptr(de), ptr(del_), ptr(dprotos), stream_of(e))
     if el is not None and del_ is None and need_el:
       del_ = torch.zeros_like(el)

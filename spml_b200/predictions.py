@@ -79,6 +79,7 @@ class Segsort(nn.Module):
     self.sem_occ_loss_weight = t.sem_occ_loss_weight
     self.img_sim_concentration = _construct_loss(t.img_sim_loss_types, t.img_sim_concentration)
     self.img_sim_loss_weight = t.img_sim_loss_weight
+    self.last_loss_total = self._contrastive_total = None
     # configured and constructed by the reference, never computed or returned
     # (segsort.py:42-47): kept for attribute compatibility.
     self.feat_aff_concentration = _construct_loss(t.feat_aff_loss_types,
@@ -149,13 +150,22 @@ class Segsort(nn.Module):
         max_groups=groups, max_rows_per_group=rows_per_group, img_tags=img_tags, ptags=ptags,
         tag_cols=(0, C) if densepose else (1, C), bank=bank, nn_tags=densepose,
         img_sim_on_plain=densepose, protos_loc=protos_loc)
-    sem_ann, sem_occ, img_sim, acc = ops.HeadLossFn.apply(e, el, targets['prototype'], spec)
+    sem_ann, sem_occ, img_sim, acc, total = ops.HeadLossFn.apply(e, el, targets['prototype'],
+                                                                 spec)
+    # the library's own `sum(losses)` (train.py:213-219) for callers that only need the sum
+    self._contrastive_total = total
     return (sem_ann if use_ann else None, sem_occ if use_occ else None,
             img_sim if use_sim else None, acc if contrast else None)
 
   def losses(self, datas, targets={}):
     """segsort.py:127-243."""
-    return self._contrastive_losses(datas, targets)
+    self._contrastive_total = None
+    out = self._contrastive_losses(datas, targets)
+    # `last_loss_total`: sem_ann + sem_occ + img_sim as train.py:213-219 adds them, computed by
+    # the same kernel (saves the caller three tiny additions and their autograd nodes)
+    self.last_loss_total = self._contrastive_total
+    self._contrastive_total = None
+    return out
 
   def forward(self, datas, targets=None, with_loss=True, with_prediction=False):
     targets = targets if targets is not None else {}
@@ -207,6 +217,7 @@ class SegsortSoftmax(Segsort):
     labels = labels.masked_fill(labels >= self.num_classes, self.semantic_ignore_index)
     ce = self.softmax_loss(logits, labels.squeeze(1).long())
     sem_ann, sem_occ, img_sim, acc = self._contrastive_losses(datas, targets)
+    self._contrastive_total = self.last_loss_total = None   # the cross-entropy joins sem_ann here
     if sem_ann is not None:
       # `sem_ann_loss += segsort; sem_ann_loss *= weight` with the SegSort term already weighted
       sem_ann = ce * self.sem_ann_loss_weight + sem_ann

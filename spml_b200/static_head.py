@@ -163,14 +163,16 @@ class StaticContrastiveHead(nn.Module):
       problem = ops.SegsortProblem(
           sem_pix, cid, psem_all, t.sem_ann_concentration, _lib.MODE_CLASS, row_index=rows,
           group_off=off, num_groups=1, n_rows=cap, max_rows_per_group=cap,
-          proto_valid=plive_all & (psem_all < C).to(torch.uint8), name='sem_ann')
+          proto_valid=plive_all & (psem_all < C).to(torch.uint8), name='sem_ann',
+          proto_grad_rows=self.m_cap)     # the bank rows behind are detached
       sem_ann = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_ann_loss_weight
     with torch.cuda.stream(streams[1]):
       # sem_occ: all live pixels x all live prototypes, image-tag masks
       all_rows = torch.stack([img_off[0], img_off[B]])
       problem = ops.SegsortProblem(
           pix_mask, cid, pmask_all, t.sem_occ_concentration, _lib.MODE_TAGS, group_off=all_rows,
-          num_groups=1, n_rows=cap, max_rows_per_group=cap, proto_valid=plive_all, name='sem_occ')
+          num_groups=1, n_rows=cap, max_rows_per_group=cap, proto_valid=plive_all, name='sem_occ',
+          proto_grad_rows=self.m_cap)
       sem_occ = ops.SegsortLossFn.apply(e, p_all, problem) * t.sem_occ_loss_weight
     with torch.cuda.stream(streams[2]):
       acc, _ = ops.topk_ranking(p_all.detach(), psem_all, p_all.detach(), psem_all, 5,

@@ -396,6 +396,38 @@ def test_segsort_sweep_corner_matches_oracle():
   assert norm_err(pc.grad.cpu(), pr.grad) < 1e-3
 
 
+@pytest.mark.parametrize('path', ['fp32', 'tc'])
+@pytest.mark.parametrize('masked', [False, True])
+@pytest.mark.parametrize('n,m,rows,dim', [(3000, 900, 300, 64), (5000, 260, 130, 66), (700, 40, 3, 32)])
+def test_segsort_prototype_gradient_rows(path, masked, n, m, rows, dim):
+  """spml_segsort_bwd_rows: the gradient of the first `rows` prototypes only (the rest of the
+  bank is detached) equals the same rows of the full gradient; the rows behind stay zero."""
+  g = torch.Generator().manual_seed(n + m + rows)
+  protos = O.l2_normalize(torch.randn(m, dim, generator=g))
+  seg = torch.randint(0, rows, (n,), generator=g)        # pixels belong to current segments
+  psem = torch.randint(0, 5, (m,), generator=g)
+  e = O.l2_normalize(protos[seg] + 0.5 * torch.randn(n, dim, generator=g))
+  valid = None
+  if masked:
+    valid = torch.rand(m, generator=g) < 0.6
+    valid[seg.unique()] = True
+    valid = cu(valid.to(torch.uint8))
+
+  def run(limit):
+    ec, pc = cu(e).requires_grad_(True), cu(protos).requires_grad_(True)
+    problem = ops.SegsortProblem(cu(psem[seg]), cu(seg), cu(psem), 10.0, _lib.MODE_CLASS,
+                                 proto_valid=valid, path=path, proto_grad_rows=limit)
+    ops.SegsortLossFn.apply(ec, pc, problem).backward()
+    return ec.grad, pc.grad
+
+  de_full, dp_full = run(None)
+  de_lim, dp_lim = run(rows)
+  assert torch.equal(de_full, de_lim)
+  assert float(dp_full[:rows].abs().max()) > 0
+  assert norm_err(dp_lim[:rows].cpu(), dp_full[:rows].cpu()) < 1e-5
+  assert float(dp_lim[rows:].abs().max()) == 0
+
+
 def test_set_segsort_wide_tags_match_oracle():
   """40 tag columns: bits 32..39 must take part (the tcgen05 epilogue compares 32-bit codes,
   so wide tag sets run on the fp32 kernels)."""
