@@ -64,7 +64,10 @@ def main():
     mark('targets')
     o = head.predictor(datas, targets)
     mark('predictor')
-    loss = sum(o[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss') if o[k] is not None)
+    loss = getattr(head.predictor, 'last_loss_total', None)     # as ContrastiveHead.forward does
+    if loss is None:
+      loss = sum(o[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss') if o[k] is not None)
+    head.predictor.last_loss_total = None
     mark('sum')
     loss.backward()
     mark('backward')

@@ -53,6 +53,12 @@ struct KmeansSmallArgs {
   float tau;
 };
 
+__device__ __forceinline__ void kms_st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void kms_st_shared_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
 __device__ __forceinline__ void kms_fence_acq_rel_gpu() {
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -121,18 +127,24 @@ __device__ __forceinline__ int kms_prefetch_tile(const KmeansArgs& p, const Tile
 // The image's unit prototypes from its fixed-point totals (common.py:39: sum / max(||sum||,
 // eps); an empty cluster is the zero vector), staged in shared memory, written to THIS CTA's
 // shared memory: fp32 rows for the exact re-check and the bf16 hi / lo operand tile.  One warp
-// per prototype, lanes across the channels.
+// per prototype, lanes across the channels, kC prototypes per warp and round.
+//
+// The rebuild sits on the critical path of every pass (nothing else can run until the
+// prototypes exist), so its dependent chains are kept short: the square root and the
+// reciprocal of the kC norms are computed once, by lanes 0..kC-1 side by side, and the
+// quotients use the branch-free shared-reciprocal division of common.cuh (sqrtf and `/` each
+// carry a range check and a slow-path call per use, which serialised the 3 kC quotient chains of
+// a warp: 3.9k cycles for 36 x 66 before, see profiles/).
 template <int kSlots>
 __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
                                                  const long long* __restrict__ totals, int kb,
                                                  float* __restrict__ pf,
                                                  uint8_t* __restrict__ b_tile,
                                                  uint32_t b_part) {
-  // kC prototypes per warp and round, interleaved: the chains (shuffle reduction, sqrt, IEEE
-  // divisions) of one prototype are ~900 cycles long with two warps per scheduler
   constexpr int kC = 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dim = p.dim;
+  const uint32_t pf_s = tc::smem_u32(pf), bt_s = tc::smem_u32(b_tile);   // 32-bit shared addresses
   for (int kbase = warp; kbase < kb; kbase += kC * kSmWarps) {
     float v[kC][kSlots], ss[kC];
 #pragma unroll
@@ -150,23 +162,32 @@ __device__ __forceinline__ void build_prototypes(const KmeansArgs& p,
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
       for (int i = 0; i < kC; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+    // lane i finishes prototype i
+    float mine = ss[0];
+#pragma unroll
+    for (int i = 1; i < kC; ++i) mine = lane == i ? ss[i] : mine;
+    const float nrm = sqrtf(mine);
+    const float div_l = nrm >= p.eps ? nrm : p.eps;     // eps = 1e-12 >= kDivMinDivisor
+    const float rcp_l = div_reciprocal(div_l);
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
       const int k = kbase + i * kSmWarps;
-      const float nrm = sqrtf(ss[i]);
-      const float div = nrm >= p.eps ? nrm : p.eps;
-      if (k < kb) {
+      const float div = __shfl_sync(0xffffffffu, div_l, i);
+      const float rcp = __shfl_sync(0xffffffffu, rcp_l, i);
+      if (k < kb) {                                  // warp-uniform
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const int d = lane + 32 * s;
+          // computed for every lane (the padding lanes hold zeros), only the stores are
+          // predicated: no branch inside the chain
+          const float u = div_by(v[i][s], div, rcp);
+          const __nv_bfloat16 h = __float2bfloat16_rn(u);
+          const __nv_bfloat16 l = __float2bfloat16_rn(u - __bfloat162float(h));
+          const uint32_t off = bt_s + operand_offset(k, d, b_part);
           if (d < dim) {
-            const float u = v[i][s] / div;
-            pf[k * dim + d] = u;
-            const __nv_bfloat16 h = __float2bfloat16_rn(u);
-            const uint32_t off = operand_offset(k, d, b_part);
-            *reinterpret_cast<__nv_bfloat16*>(b_tile + off) = h;
-            *reinterpret_cast<__nv_bfloat16*>(b_tile + off + b_part) =
-                __float2bfloat16_rn(u - __bfloat162float(h));
+            kms_st_shared_f32(pf_s + (uint32_t)(k * dim + d) * 4u, u);
+            kms_st_shared_u16(off, __bfloat16_as_ushort(h));
+            kms_st_shared_u16(off + b_part, __bfloat16_as_ushort(l));
           }
         }
       }

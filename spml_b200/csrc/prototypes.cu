@@ -68,8 +68,14 @@ __global__ void prototype_finalize_kernel(const long long* __restrict__ sums,
   const bool ok = nrm >= eps;
   const float div = ok ? nrm : eps;
   const float nan = __int_as_float(0x7fc00000);
-  for (int d = lane; d < dim; d += 32)
-    protos[row * dim + d] = bad ? nan : from_fixed(sums[row * dim + d]) / div;
+  if (eps >= kDivMinDivisor) {             // (kernel-uniform) the shared-reciprocal division
+    const float r = div_reciprocal(div);
+    for (int d = lane; d < dim; d += 32)
+      protos[row * dim + d] = bad ? nan : div_by(from_fixed(sums[row * dim + d]), div, r);
+  } else {
+    for (int d = lane; d < dim; d += 32)
+      protos[row * dim + d] = bad ? nan : from_fixed(sums[row * dim + d]) / div;
+  }
   if (lane == 0 && norms) norms[row] = bad ? nan : (ok ? nrm : -eps);
 }
 

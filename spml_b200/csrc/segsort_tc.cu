@@ -24,6 +24,8 @@
 #include "tc_common.cuh"
 #include "segsort_tc.h"
 
+#include <chrono>
+
 namespace spml {
 
 // ------------------------------------------------------------------------- host: tensor map
@@ -1265,6 +1267,57 @@ int segsort_bwd_tc(const spml_segsort_desc& d, const TcPlan& p, const float* sta
 }
 
 }  // namespace spml
+
+// Host-side cost of the driver calls a stage-group entry makes, in nanoseconds per call
+// (scripts/host_costs.py): out = {tensor-map encode, cudaFuncSetAttribute, empty kernel
+// launch, 16-byte cudaMemsetAsync, event record + stream wait}.
+namespace spml {
+__global__ void empty_kernel() {}
+}
+extern "C" int spml_debug_host_costs(double* out, void* stream) {
+  using namespace spml;
+  using clk = std::chrono::steady_clock;
+  cudaStream_t st = as_stream(stream);
+  const int n = 2000;
+  void* buf = nullptr;
+  SPML_CUDA(cudaMalloc(&buf, 1 << 20));
+  cudaEvent_t ev;
+  SPML_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaStream_t side;
+  SPML_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  auto ns = [&](clk::time_point t0) {
+    return std::chrono::duration<double, std::nano>(clk::now() - t0).count() / n;
+  };
+  CUtensorMap map;
+  auto t0 = clk::now();
+  for (int i = 0; i < n; ++i) make_tensor_map_bf16_2d(&map, buf, 64, 1024 + i % 7, 128, 64, 128);
+  out[0] = ns(t0);
+  t0 = clk::now();
+  for (int i = 0; i < n; ++i)
+    cudaFuncSetAttribute(empty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + (i & 1));
+  out[1] = ns(t0);
+  SPML_CUDA(cudaStreamSynchronize(st));
+  t0 = clk::now();
+  for (int i = 0; i < n; ++i) empty_kernel<<<1, 32, 0, st>>>();
+  out[2] = ns(t0);
+  SPML_CUDA(cudaStreamSynchronize(st));
+  t0 = clk::now();
+  for (int i = 0; i < n; ++i) cudaMemsetAsync(buf, 0, 16, st);
+  out[3] = ns(t0);
+  SPML_CUDA(cudaStreamSynchronize(st));
+  t0 = clk::now();
+  for (int i = 0; i < n; ++i) {
+    cudaEventRecord(ev, st);
+    cudaStreamWaitEvent(side, ev, 0);
+  }
+  out[4] = ns(t0);
+  SPML_CUDA(cudaStreamSynchronize(st));
+  SPML_CUDA(cudaStreamSynchronize(side));
+  cudaStreamDestroy(side);
+  cudaEventDestroy(ev);
+  cudaFree(buf);
+  return SPML_OK;
+}
 
 #ifdef SPML_TC_TRACE
 extern "C" int spml_debug_tc_trace(long long* host_out) {

@@ -233,7 +233,7 @@ std::vector<Tensor> gather_bwd(const Tensor& fbuf, const Tensor& cid, const OptT
 
 // One forward / backward pair of Segsort*.losses(): owns the argument struct and keeps every
 // tensor whose address is in it alive until the backward has been enqueued.
-struct HeadCall {
+struct HeadCall : torch::CustomClassHolder {
   spml_head_args a{};
   std::vector<Tensor> keep;
   Tensor state, e, el, protos;
@@ -364,6 +364,146 @@ struct HeadCall {
   }
 };
 
+
+// ------------------------------------------------------------------------- autograd nodes
+//
+// The three stage groups as C++ autograd functions: torch.autograd.Function.apply costs
+// ~20 us of Python per call and the engine re-enters the interpreter for every backward; at
+// batch 1 the host is the critical path of the step (profiles/r2_step_profile_b1.txt), so the
+// nodes live here and Python only sees plain functions.  ops.py keeps equivalent
+// torch.autograd.Function classes over ctypes for the case that this module is not built.
+
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+struct SegmentParams {
+  OptTensor loc, labels, sem, inst, ignore_dev, k_per_image;
+  Tensor seeds, status;
+  int64_t divisor, semantic_ignore, ignore_index, num_k, iterations, batch_index_offset;
+  bool has_ignore;
+};
+
+struct SegmentResult {
+  int64_t rows = 0, segments = 0, bits = 0;
+  Tensor ibuf;
+};
+
+struct SegmentFn : public torch::autograd::Function<SegmentFn> {
+  static variable_list forward(AutogradContext* ctx, const Tensor& emb, const SegmentParams* p,
+                               SegmentResult* r) {
+    auto res = segment_fwd(emb, p->loc, p->labels, p->sem, p->inst, p->divisor,
+                           p->semantic_ignore, p->has_ignore, p->ignore_index, p->ignore_dev,
+                           p->seeds, p->k_per_image, p->num_k, p->iterations,
+                           p->batch_index_offset, p->status);
+    std::vector<Tensor>& outs = std::get<0>(res);
+    Tensor ibuf = outs.back();
+    outs.pop_back();
+    Tensor fbuf = outs.back();
+    outs.pop_back();
+    r->rows = std::get<1>(res), r->segments = std::get<2>(res), r->bits = std::get<3>(res);
+    r->ibuf = ibuf;
+    const int64_t B = emb.size(0);
+    const int64_t loc_ch = p->loc.has_value() && p->loc->defined() ? p->loc->size(3) : 0;
+    // the backward reads e, el, the two norms and the pixel -> row map: all inside these two
+    // buffers (kept whole; the addresses are re-derived from the dims)
+    ctx->save_for_backward({fbuf, ibuf});
+    ctx->saved_data["dims"] = std::vector<int64_t>{B, emb.size(1), loc_ch, emb.size(2), emb.size(3),
+                                                   (B + 2 + 4 + 3) / 4 * 4};
+    ctx->mark_non_differentiable(variable_list(outs.begin() + 2, outs.end()));
+    ctx->set_materialize_grads(false);
+    return outs;
+  }
+
+  static variable_list backward(AutogradContext* ctx, variable_list g) {
+    if (!g[0].defined() && !g[1].defined()) return {Tensor(), Tensor(), Tensor()};
+    const auto saved = ctx->get_saved_variables();
+    const auto d = ctx->saved_data["dims"].toIntVector();
+    return {segment_bwd(saved[0], saved[1], g[0], g[1], d[0], d[1], d[2], d[3], d[4], d[5]),
+            Tensor(), Tensor()};
+  }
+};
+
+std::tuple<std::vector<Tensor>, int64_t, int64_t, int64_t, Tensor> segment(
+    const Tensor& emb, const OptTensor& loc, const OptTensor& labels, const OptTensor& sem,
+    const OptTensor& inst, int64_t divisor, int64_t semantic_ignore, bool has_ignore,
+    int64_t ignore_index, const OptTensor& ignore_dev, const Tensor& seeds,
+    const OptTensor& k_per_image, int64_t num_k, int64_t iterations, int64_t batch_index_offset,
+    const Tensor& status) {
+  SegmentParams p{loc, labels, sem, inst, ignore_dev, k_per_image, seeds, status, divisor,
+                  semantic_ignore, ignore_index, num_k, iterations, batch_index_offset, has_ignore};
+  SegmentResult r;
+  variable_list outs = SegmentFn::apply(emb, &p, &r);
+  return {outs, r.rows, r.segments, r.bits, r.ibuf};
+}
+
+struct GatherParams {
+  Tensor cid, bid, sem, inst, status;
+  int64_t m;
+};
+
+struct GatherFn : public torch::autograd::Function<GatherFn> {
+  static variable_list forward(AutogradContext* ctx, const Tensor& e, const Tensor& el,
+                               const GatherParams* p) {
+    std::vector<Tensor> o = gather_fwd(e, el, p->cid, p->bid, p->sem, p->inst, p->m, p->status);
+    ctx->save_for_backward({o[5], o[6]});        // fbuf, cluster ids
+    ctx->saved_data["dims"] = std::vector<int64_t>{p->m, e.size(1), el.size(1)};
+    ctx->mark_non_differentiable({o[2], o[3], o[4]});
+    ctx->set_materialize_grads(false);   // an unused prototype set costs nothing in the backward
+    o.resize(5);
+    return o;
+  }
+
+  static variable_list backward(AutogradContext* ctx, variable_list g) {
+    if (!g[0].defined() && !g[1].defined()) return {Tensor(), Tensor(), Tensor()};
+    const auto saved = ctx->get_saved_variables();
+    const auto d = ctx->saved_data["dims"].toIntVector();
+    std::vector<Tensor> r = gather_bwd(saved[0], saved[1], g[0], g[1], d[0], d[1], d[2]);
+    return {r[0], r[1], Tensor()};
+  }
+};
+
+std::vector<Tensor> gather(const Tensor& e, const Tensor& el, const Tensor& cid, const Tensor& bid,
+                           const Tensor& sem, const Tensor& inst, int64_t m, const Tensor& status) {
+  GatherParams p{cid, bid, sem, inst, status, m};
+  return GatherFn::apply(e, el, &p);
+}
+
+struct HeadFn : public torch::autograd::Function<HeadFn> {
+  static variable_list forward(AutogradContext* ctx, const Tensor& e, const OptTensor& el,
+                               const Tensor& protos, const c10::intrusive_ptr<HeadCall>& call,
+                               const Tensor* status) {
+    Tensor out = call->forward(e, el, protos, *status);
+    ctx->saved_data["call"] = at::IValue::make_capsule(call);
+    ctx->saved_data["has_el"] = el.has_value() && el->defined();
+    ctx->set_materialize_grads(false);
+    variable_list outs = out.unbind(0);          // sem_ann, sem_occ, img_sim, accuracy, sum
+    ctx->mark_non_differentiable({outs[3]});
+    return outs;
+  }
+
+  static variable_list backward(AutogradContext* ctx, variable_list g) {
+    variable_list none(5);
+    if (!g[0].defined() && !g[1].defined() && !g[2].defined() && !g[4].defined()) return none;
+    auto call = c10::static_intrusive_pointer_cast<HeadCall>(ctx->saved_data["call"].toCapsule());
+    const bool has_el = ctx->saved_data["has_el"].toBool();
+    // needs_input_grad counts the tensor inputs only: e, [el,] protos
+    const bool need_e = ctx->needs_input_grad(0);
+    const bool need_el = has_el && ctx->needs_input_grad(1);
+    const bool need_p = ctx->needs_input_grad(has_el ? 2 : 1);
+    auto opt = [](const Tensor& t) { return t.defined() ? OptTensor(t) : OptTensor(); };
+    std::vector<Tensor> r = call->backward(opt(g[0]), opt(g[1]), opt(g[2]), opt(g[4]), need_p);
+    none[0] = need_e ? r[0] : Tensor();
+    none[1] = need_el ? r[1] : Tensor();
+    none[2] = r[2];
+    return none;
+  }
+};
+
+std::vector<Tensor> head(const Tensor& e, const OptTensor& el, const Tensor& protos,
+                         const c10::intrusive_ptr<HeadCall>& call, const Tensor& status) {
+  return HeadFn::apply(e, el, protos, call, &status);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -373,14 +513,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("segment_bwd", &segment_bwd);
   m.def("gather_fwd", &gather_fwd);
   m.def("gather_bwd", &gather_bwd);
-  pybind11::class_<HeadCall>(m, "HeadCall")
-      .def(pybind11::init<const Tensor&, const OptTensor&, const OptTensor&, const OptTensor&,
-                          const Tensor&, const OptTensor&, const OptTensor&, int64_t, int64_t,
-                          std::vector<double>, std::vector<double>, int64_t, int64_t,
-                          const OptTensor&, const OptTensor&, int64_t, int64_t,
-                          const std::vector<Tensor>&, const std::vector<Tensor>&,
-                          const std::vector<Tensor>&, const std::vector<Tensor>&,
-                          const std::vector<Tensor>&, bool, bool, const OptTensor&, double>())
+  m.def("segment", &segment);
+  m.def("gather", &gather);
+  m.def("head", &head);
+  pybind11::class_<HeadCall, c10::intrusive_ptr<HeadCall>>(m, "HeadCall")
+      .def(pybind11::init([](const Tensor& cid, const OptTensor& bid, const OptTensor& sem,
+                             const OptTensor& inst, const Tensor& psem, const OptTensor& pinst,
+                             const OptTensor& pbid, int64_t num_classes, int64_t enable,
+                             std::vector<double> kappas, std::vector<double> weights,
+                             int64_t max_groups, int64_t max_rows_per_group,
+                             const OptTensor& img_tags, const OptTensor& ptags, int64_t tag_col0,
+                             int64_t tag_col1, const std::vector<Tensor>& bank_protos,
+                             const std::vector<Tensor>& bank_sems,
+                             const std::vector<Tensor>& bank_bids,
+                             const std::vector<Tensor>& bank_tags,
+                             const std::vector<Tensor>& bank_locs, bool nn_tags,
+                             bool img_sim_on_plain, const OptTensor& protos_loc,
+                             double nn_threshold) {
+        return c10::make_intrusive<HeadCall>(
+            cid, bid, sem, inst, psem, pinst, pbid, num_classes, enable, kappas, weights,
+            max_groups, max_rows_per_group, img_tags, ptags, tag_col0, tag_col1, bank_protos,
+            bank_sems, bank_bids, bank_tags, bank_locs, nn_tags, img_sim_on_plain, protos_loc,
+            nn_threshold);
+      }))
       .def("forward", &HeadCall::forward)
       .def("backward", &HeadCall::backward);
 }

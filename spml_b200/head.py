@@ -81,7 +81,7 @@ class ContrastiveHead(nn.Module):
                       'densepose': predictions.SegsortSoftmaxDensepose}[self.variant](config)
     self.memory_bank_size = int(getattr(config.train, 'memory_bank_size', 0))
     self.memory_banks = {}
-    self._last_targets = None
+    object.__setattr__(self, '_last_targets', None)
     self._last_batch = 0
 
   def forward(self, embedding, semantic_label, instance_label, semantic_tag,
@@ -126,14 +126,16 @@ class ContrastiveHead(nn.Module):
     total = getattr(self.predictor, 'last_loss_total', None)
     if total is not None:
       # the head kernel already added the losses it produced (same order, same fp32 adds)
-      self.predictor.last_loss_total = None
+      object.__setattr__(self.predictor, 'last_loss_total', None)
       out['loss'] = total
     else:
       losses = [out[k] for k in ('sem_ann_loss', 'sem_occ_loss', 'img_sim_loss')
                 if out.get(k, None) is not None]
       out['loss'] = sum(losses)                                        # train.py:213-219
     out['datas'], out['targets'] = datas, targets
-    self._last_targets, self._last_batch = targets, embedding.shape[0]
+    # (object.__setattr__: nn.Module.__setattr__ costs ~5 us per assignment)
+    object.__setattr__(self, '_last_targets', targets)
+    object.__setattr__(self, '_last_batch', embedding.shape[0])
     return out
 
   @torch.no_grad()
@@ -147,12 +149,12 @@ class ContrastiveHead(nn.Module):
     for k, v in self._last_targets.items():
       if 'prototype' in k and 'memory' not in k and torch.is_tensor(v):
         bank = self.memory_banks.setdefault('memory_' + k, [])
-        bank.append(v.detach())
+        bank.append(v.detach() if v.requires_grad else v)
         if len(bank) > self.memory_bank_size:
           self.memory_banks['memory_' + k] = bank[1:]
     key = 'memory_prototype_batch_index'
-    if key in self.memory_banks:
+    if self.memory_banks.get(key):
       stride = self._last_batch * num_replicas
       # one multi-tensor launch for the whole list
       self.memory_banks[key] = list(torch._foreach_add(self.memory_banks[key], stride))
-    self._last_targets = None
+    object.__setattr__(self, '_last_targets', None)

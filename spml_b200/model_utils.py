@@ -51,7 +51,7 @@ def gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, clu
     # check on the device that every segment carries one (batch, sem, inst) triple, i.e. that
     # these really are the labels the ids were made from (ops.check_status reports it).
     new_cid = cid
-    protos, protos_loc, p_sem, p_inst, p_bid = ops.GatherPrototypesFn.apply(
+    protos, protos_loc, p_sem, p_inst, p_bid = ops.gather_prototypes_stage(
         e, el, cid, bid, sem, inst, meta.num_segments)
   else:
     if cid.numel() == 0:

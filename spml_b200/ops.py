@@ -846,3 +846,46 @@ class HeadLossFn(torch.autograd.Function):
     if el is not None and del_ is None and need_el:
       del_ = torch.zeros_like(el)
     return (de if need_e else None), (del_ if need_el else None), dprotos, None
+
+
+# ------------------------------------------------------------------------------ entry points
+#
+# What the operator modules call.  With the ATen binding the autograd nodes are C++
+# (binding.cpp: SegmentFn / GatherFn / HeadFn: no torch.autograd.Function.apply, no Python in
+# the backward); without it the torch.autograd.Function classes above do the same over ctypes.
+
+
+def segment_by_kmeans_stage(emb, loc, labels, sem, inst, divisor, semantic_ignore, ignore_index,
+                            seeds, k_per_image, num_k, iterations, batch_index_offset):
+  """-> (outputs, rows kept, segments, int32 buffer that starts with the image offsets)."""
+  if _C is not None:
+    ignore_dev = ignore_index if torch.is_tensor(ignore_index) else None
+    outs, rows, segments, bits, ibuf = _C.segment(
+        emb, loc, labels, sem, inst, int(divisor) if divisor else 0,
+        int(semantic_ignore) if semantic_ignore is not None else 0,
+        ignore_index is not None, 0 if (ignore_dev is not None or ignore_index is None)
+        else int(ignore_index), ignore_dev, seeds, k_per_image, int(num_k), int(iterations),
+        int(batch_index_offset), status_word(emb.device))
+    if bits:
+      raise _status_error(bits)
+    return tuple(outs), rows, segments, ibuf
+  box = []
+  outs = SegmentByKmeansFn.apply(emb, loc, labels, sem, inst, divisor, semantic_ignore,
+                                 ignore_index, seeds, k_per_image, num_k, iterations,
+                                 batch_index_offset, box)
+  rows, segments, ibuf = box[0]
+  return outs, rows, segments, ibuf
+
+
+def gather_prototypes_stage(e, el, cid, bid, sem, inst, m):
+  """-> (prototypes, prototypes_with_loc, semantic, instance, batch index of every segment)."""
+  if _C is not None:
+    return _C.gather(e, el, cid, bid, sem, inst, int(m), status_word(e.device))
+  return GatherPrototypesFn.apply(e, el, cid, bid, sem, inst, m)
+
+
+def head_losses_stage(e, el, protos, spec):
+  """-> (sem_ann, sem_occ, img_sim, accuracy, sum of the enabled losses)."""
+  if spec.call is not None:
+    return _C.head(e, el, protos, spec.call, status_word(e.device))
+  return HeadLossFn.apply(e, el, protos, spec)

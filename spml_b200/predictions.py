@@ -150,21 +150,22 @@ class Segsort(nn.Module):
         max_groups=groups, max_rows_per_group=rows_per_group, img_tags=img_tags, ptags=ptags,
         tag_cols=(0, C) if densepose else (1, C), bank=bank, nn_tags=densepose,
         img_sim_on_plain=densepose, protos_loc=protos_loc)
-    sem_ann, sem_occ, img_sim, acc, total = ops.HeadLossFn.apply(e, el, targets['prototype'],
-                                                                 spec)
+    sem_ann, sem_occ, img_sim, acc, total = ops.head_losses_stage(e, el, targets['prototype'],
+                                                                  spec)
     # the library's own `sum(losses)` (train.py:213-219) for callers that only need the sum
-    self._contrastive_total = total
+    # (object.__setattr__: nn.Module.__setattr__ costs ~5 us per assignment)
+    object.__setattr__(self, '_contrastive_total', total)
     return (sem_ann if use_ann else None, sem_occ if use_occ else None,
             img_sim if use_sim else None, acc if contrast else None)
 
   def losses(self, datas, targets={}):
     """segsort.py:127-243."""
-    self._contrastive_total = None
+    object.__setattr__(self, '_contrastive_total', None)
     out = self._contrastive_losses(datas, targets)
     # `last_loss_total`: sem_ann + sem_occ + img_sim as train.py:213-219 adds them, computed by
     # the same kernel (saves the caller three tiny additions and their autograd nodes)
-    self.last_loss_total = self._contrastive_total
-    self._contrastive_total = None
+    object.__setattr__(self, 'last_loss_total', self._contrastive_total)
+    object.__setattr__(self, '_contrastive_total', None)
     return out
 
   def forward(self, datas, targets=None, with_loss=True, with_prediction=False):
@@ -217,7 +218,8 @@ class SegsortSoftmax(Segsort):
     labels = labels.masked_fill(labels >= self.num_classes, self.semantic_ignore_index)
     ce = self.softmax_loss(logits, labels.squeeze(1).long())
     sem_ann, sem_occ, img_sim, acc = self._contrastive_losses(datas, targets)
-    self._contrastive_total = self.last_loss_total = None   # the cross-entropy joins sem_ann here
+    object.__setattr__(self, '_contrastive_total', None)    # the cross-entropy joins sem_ann here
+    object.__setattr__(self, 'last_loss_total', None)
     if sem_ann is not None:
       # `sem_ann_loss += segsort; sem_ann_loss *= weight` with the SegSort term already weighted
       sem_ann = ce * self.sem_ann_loss_weight + sem_ann

@@ -268,12 +268,10 @@ def segment_clusters(embeddings, labels=None, num_clusters=[5, 5], cluster_indic
     labels = torch.zeros((B, H, W), dtype=torch.long, device=dev)
   if batch_index_offset is None:
     batch_index_offset = B * (dev.index or 0)                           # :376-377
-  box = []
-  out = ops.SegmentByKmeansFn.apply(
+  out, rows, segments, img_off = ops.segment_by_kmeans_stage(
       embeddings, local_features, None if packed else labels, semantic_labels, instance_labels,
       label_divisor, semantic_ignore_index, ignore_index, seeds, k_per_image, num_k, iterations,
-      batch_index_offset, box)
-  rows, segments, img_off = box[0]
+      batch_index_offset)
   _register_segments(out[3], SegmentMeta(segments, rows, img_off, B, batch_index_offset))
   return out
 
