@@ -28,3 +28,30 @@ for it in range(w.iterations + 1):
   ev = ' '.join('%s@%d' % (names[k], int(r[k] - r[0])) for k in (1, 2, 11, 12, 13, 3, 4, 5, 6, 10, 7, 8, 9) if r[k] != 0)
   nxt = int(t[it + 1][0] - r[0]) if it < w.iterations else 0
   print('it %2d  %s   next pass @%d' % (it, ev, nxt))
+
+# ---- every CTA: busy time of a pass = (own "counted") - (own "done seen"); the pass is as long
+# as the slowest CTA.  Phase lengths: median / max over the CTAs.
+allb = (ctypes.c_longlong * (160 * 256))()
+lib.spml_debug_kms_trace_all.argtypes = [ctypes.c_void_p]
+assert lib.spml_debug_kms_trace_all(allb) == 0
+a = torch.tensor(list(allb)).view(160, 16, 16)
+live = (a[:, 1, 9] != 0).nonzero().flatten()
+order = (2, 11, 12, 13, 3, 4, 5, 6, 7, 8, 9)
+print('\nper-CTA phase lengths over %d CTAs (cycles): median / max [CTA of the max]' % live.numel())
+for it in range(1, w.iterations):
+  r = a[live, it]
+  parts = []
+  prev = r[:, 2]
+  for k in order[1:]:
+    d = r[:, k] - prev
+    parts.append('%s %d/%d[%d]' % (names[k], int(d.median()), int(d.max()), int(live[d.argmax()])))
+    prev = r[:, k]
+  amb = r[:, 14]
+  parts.append('ambiguous rows %d total, max %d[%d]' % (int(amb.sum()), int(amb.max()), int(live[amb.argmax()])))
+  parts.append('exact row (warp 0) %d' % int(r[:, 15].max()))
+  busy = r[:, 9] - r[:, 2]
+  wait = r[:, 2] - a[live, it - 1, 9] if it > 1 else None
+  print('it %2d busy %d/%d[%d]%s  %s' % (
+      it, int(busy.median()), int(busy.max()), int(live[busy.argmax()]),
+      '' if wait is None else ' waited %d/%d min %d' % (int(wait.median()), int(wait.max()), int(wait.min())),
+      ' '.join(parts)))

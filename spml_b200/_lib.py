@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPML_B200_LIB: another build of the same library (e.g. a -DSPML_KM_TRACE build for scripts/)
 LIB_PATH = os.environ.get('SPML_B200_LIB') or os.path.join(_HERE, 'libspml_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t

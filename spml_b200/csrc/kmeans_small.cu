@@ -36,11 +36,24 @@ constexpr int kSmMaxTilesPerFlush = 24;    // 2^19 * 128 * 24 < 2^31: the hi hal
 
 #ifdef SPML_KM_TRACE
 __device__ long long g_kms_trace[16 * 16];
+// every CTA's stamps of its last tile of each pass: [CTA][pass][slot] (SM-local clocks: only
+// differences inside one CTA mean something; "done seen" is the common reference of a pass)
+__device__ long long g_kms_trace_all[160 * 16 * 16];
 #define KMS(slot)                                                                          \
   do {                                                                                     \
-    if (lt0 == 0 && lt1 > 0 && threadIdx.x == 0 && it < 16) g_kms_trace[it * 16 + (slot)] = clock64(); \
+    if (threadIdx.x == 0 && it < 16) {                                                     \
+      const long long c__ = clock64();                                                     \
+      if (lt0 == 0 && lt1 > 0) g_kms_trace[it * 16 + (slot)] = c__;                        \
+      if (blockIdx.x < 160) g_kms_trace_all[(blockIdx.x * 16 + it) * 16 + (slot)] = c__;   \
+    }                                                                                      \
+  } while (0)
+#define KMS_VAL(slot, v)                                                                   \
+  do {                                                                                     \
+    if (threadIdx.x == 0 && it < 16 && blockIdx.x < 160)                                   \
+      g_kms_trace_all[(blockIdx.x * 16 + it) * 16 + (slot)] = (v);                         \
   } while (0)
 #else
+#define KMS_VAL(slot, v) do { } while (0)
 #define KMS(slot) do { } while (0)
 #endif
 
@@ -301,6 +314,100 @@ __device__ __forceinline__ bool accumulate_tile(int sorted, int dim, const float
   return bad;
 }
 
+// Exact scores of one row against the prototypes lane, lane + 32, ... (kChains of them per
+// lane): the very fmaf chain of the fp32 kernel (d ascending from 0), so the label of an
+// ambiguous row is the one the fp32 path (and the reference) gives.  The chains of a lane are
+// independent and the loads of eight steps are issued ahead of the arithmetic: a straggler row
+// costs ~0.5k cycles instead of 3.3k (one such row held up the whole pass, profiles/).
+// Returns the lane's best (score, index), first index on ties.
+template <int kChains>
+__device__ __forceinline__ void exact_best(const float* __restrict__ xr,
+                                           const float* __restrict__ pf, int dim, int kb, int lane,
+                                           float& bv, int& bk) {
+  float acc[kChains];
+  const float* pk[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) {
+    acc[c] = 0.f;
+    pk[c] = pf + min(lane + 32 * c, kb - 1) * dim;     // out-of-range lanes redo the last row
+  }
+  int d = 0;
+  // a single warp is bound by the number of shared-memory instructions it can issue (scalar
+  // loads: 2.1k cycles for 36 x 66), so the rows are read as float2 where they are 8-byte
+  // aligned (even dim: every row of both arrays is)
+  if ((dim & 1) == 0 && ((tc::smem_u32(xr) | tc::smem_u32(pf)) & 7u) == 0) {
+#pragma unroll 2
+    for (; d + 8 <= dim; d += 8) {
+      float2 xv[4], pv[kChains][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float2*>(xr + d + 2 * j);
+#pragma unroll
+      for (int c = 0; c < kChains; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pv[c][j] = *reinterpret_cast<const float2*>(pk[c] + d + 2 * j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) acc[c] = fmaf(xv[j].x, pv[c][j].x, acc[c]);
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) acc[c] = fmaf(xv[j].y, pv[c][j].y, acc[c]);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (; d + 8 <= dim; d += 8) {
+      float xv[8], pv[kChains][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = xr[d + j];
+#pragma unroll
+      for (int c = 0; c < kChains; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pv[c][j] = pk[c][d + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) acc[c] = fmaf(xv[j], pv[c][j], acc[c]);
+    }
+  }
+  for (; d < dim; ++d) {
+    const float x = xr[d];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) acc[c] = fmaf(x, pk[c][d], acc[c]);
+  }
+  bv = -INFINITY;
+  bk = 0;
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) {
+    const int k = lane + 32 * c;
+    if (k < kb && acc[c] > bv) bv = acc[c], bk = k;
+  }
+}
+
+// The exact label of one row (one warp).  NOT inlined: the recheck is rare (a few rows of the
+// whole grid per pass), so on most SMs its instructions are cold when it finally runs, and
+// every instruction-cache miss is an L2 round trip (~1k cycles, 2-4 of them measured per row
+// on top of the 1.3k cycles of the chain itself, and the whole pass waits for that one row).
+// The kernel runs it once on scratch data at its start, through this same copy of the code,
+// which takes the misses off the passes (a row costs 1.8-2.2k cycles afterwards).
+__device__ __noinline__ int exact_row_label(const float* xr, const float* pf, int dim, int kb,
+                                            int lane) {
+  float bv;
+  int bk;
+  switch ((kb + 31) >> 5) {
+    case 1: exact_best<1>(xr, pf, dim, kb, lane, bv, bk); break;
+    case 2: exact_best<2>(xr, pf, dim, kb, lane, bv, bk); break;
+    case 3: exact_best<3>(xr, pf, dim, kb, lane, bv, bk); break;
+    default: exact_best<4>(xr, pf, dim, kb, lane, bv, bk); break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    if (ov > bv || (ov == bv && ok < bk)) bv = ov, bk = ok;
+  }
+  return bk;
+}
+
 #define KMS_SLOT_SWITCH(dim, CALL)           \
   switch (((dim) + 31) >> 5) {               \
     case 1: { constexpr int kS = 1; CALL; } break; \
@@ -313,13 +420,13 @@ __device__ __forceinline__ bool accumulate_tile(int sorted, int dim, const float
 __global__ void __launch_bounds__(kGemmThreads, 1)
 kmeans_small_kernel(const KmeansSmallArgs a) {
   extern __shared__ uint8_t kms_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_t_full;
+  __shared__ __align__(8) uint64_t bar_t_full, bar_stage;
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_lab[BM], s_old[BM];
   __shared__ float s_b1[BM], s_b2[BM];
   __shared__ int s_k1[BM];
   __shared__ int s_amb[BM], s_chg[BM];
-  __shared__ int s_namb, s_nchg, s_sorted;
+  __shared__ int s_namb, s_nchg, s_sorted, s_warm;
   __shared__ int s_cnt[kSmBN];
   __shared__ unsigned char s_order[BM];
 
@@ -363,6 +470,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
 
   if (tid == 0) {
     tc::mbar_init(&bar_t_full, 1);
+    tc::mbar_init(&bar_stage, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&s_tmem_base, 2 * kSmBN);   // one accumulator [hh + lh | hl]
@@ -374,6 +482,12 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // instruction-cache warm-up of the exact recheck (see exact_row_label) on whatever bytes
+  // the prototype rows hold right now; the result goes nowhere
+  if (warp == kSmWarps - 1) {
+    const int warm = exact_row_label(pf, pf, dim, K, lane);
+    if (lane == 0) s_warm = warm;
+  }
 
   const uint32_t idesc = a.bn == 64 ? tc::umma_idesc_bf16(BM, 64, 0, 0)
                                     : tc::umma_idesc_bf16(BM, 128, 0, 0);
@@ -385,6 +499,7 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
   const uint32_t b_lo = tc::umma_desc_lo(tc::smem_u32(b_tile), 16);
 
   uint32_t q = 0;   // tiles this CTA has pushed through the accumulator so far (barrier parity)
+  uint32_t stage_phase = 0;   // parity of bar_stage (one bulk copy of the totals per rebuild)
   const bool pf_on = a.prefetch && !resident && lt0 < lt1;
   int cur = 0, lead_cur = 0, lead_nxt = 0;
   if (pf_on) {
@@ -506,32 +621,43 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
             }
             kms_fence_acq_rel_gpu();
           }
+          tc::fence_proxy_async();   // this thread's zeroing of s_hi / s_lo -> the bulk copy below
           __syncthreads();
           KMS(2);
-          // ---- the image's totals after pass it - 1: one flat batch of L2 loads into the
-          // (currently all-zero) s_hi / s_lo bytes
-          // Every CTA of the image reads the SAME K x dim words at the same moment; walking
-          // them in the same order serialises ~100 SMs on a handful of L2 lines at a time
-          // (measured: 5-9k cycles for 19 KB).  Each CTA starts at its own rotation instead.
+          // ---- the image's totals after pass it - 1 into the (currently all-zero) s_hi / s_lo
+          // bytes.  Every CTA of the image reads the SAME K x dim words at the same moment.
           const long long* tot_prev = p.sums + (size_t)(it - 1) * per_iter + (size_t)b * per_img;
-          const int rot = (int)(((unsigned)blockIdx.x * 2654435761u >> 8) % (unsigned)per_img) & ~31;
-          for (int i0 = 0; i0 < per_img; i0 += 12 * kGemmThreads) {
-            long long r12[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-              int i = i0 + j * kGemmThreads + tid;
-              const bool in = i < per_img;
-              i += rot;
-              i -= i >= per_img ? per_img : 0;
-              r12[j] = in ? __ldcg(tot_prev + i) : 0;
+          if ((per_img & 1) == 0) {
+            // one bulk copy (16-byte granular: per_img even makes source and size aligned)
+            if (tid == 0) {
+              tc::fence_proxy_async_all();
+              tc::mbar_expect_tx(&bar_stage, (uint32_t)per_img * 8u);
+              tc::bulk_load(s_tot, tot_prev, (uint32_t)per_img * 8u, &bar_stage);
             }
+            tc::mbar_wait(&bar_stage, stage_phase);
+            stage_phase ^= 1u;
+          } else {
+            // walking the words in the same order serialises ~100 SMs on a handful of L2 lines
+            // at a time (measured: 5-9k cycles for 19 KB): each CTA starts at its own rotation
+            const int rot = (int)(((unsigned)blockIdx.x * 2654435761u >> 8) % (unsigned)per_img) & ~31;
+            for (int i0 = 0; i0 < per_img; i0 += 12 * kGemmThreads) {
+              long long r12[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-              int i = i0 + j * kGemmThreads + tid;
-              const bool in = i < per_img;
-              i += rot;
-              i -= i >= per_img ? per_img : 0;
-              if (in) s_tot[i] = r12[j];
+              for (int j = 0; j < 12; ++j) {
+                int i = i0 + j * kGemmThreads + tid;
+                const bool in = i < per_img;
+                i += rot;
+                i -= i >= per_img ? per_img : 0;
+                r12[j] = in ? __ldcg(tot_prev + i) : 0;
+              }
+#pragma unroll
+              for (int j = 0; j < 12; ++j) {
+                int i = i0 + j * kGemmThreads + tid;
+                const bool in = i < per_img;
+                i += rot;
+                i -= i >= per_img ? per_img : 0;
+                if (in) s_tot[i] = r12[j];
+              }
             }
           }
           __syncthreads();
@@ -635,27 +761,19 @@ kmeans_small_kernel(const KmeansSmallArgs a) {
         __syncthreads();
         const int namb = s_namb;
         KMS(5);
+        KMS_VAL(14, namb);
         // exact re-check: the very fmaf chain of the fp32 kernel (d ascending from 0), first
         // index on ties, against the fp32 prototypes in shared memory
         for (int i = warp; i < namb; i += kSmWarps) {
           const int r = s_amb[i];
-          const float* xr = xs + r * dim;
-          float bv = -INFINITY;
-          int bk = 0;
-          for (int k = lane; k < kb; k += 32) {
-            float accv = 0.f;
-            const float* pk = pf + k * dim;
-#pragma unroll 4
-            for (int d = 0; d < dim; ++d) accv = fmaf(xr[d], pk[d], accv);
-            if (accv > bv) bv = accv, bk = k;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (ov > bv || (ov == bv && ok < bk)) bv = ov, bk = ok;
-          }
+#ifdef SPML_KM_TRACE
+          const long long t0__ = clock64();
+#endif
+          const int bk = exact_row_label(xs + r * dim, pf, dim, kb, lane);
           if (lane == 0) s_lab[r] = bk;
+#ifdef SPML_KM_TRACE
+          KMS_VAL(15, clock64() - t0__);
+#endif
         }
         __syncthreads();
         KMS(6);
@@ -791,6 +909,11 @@ int kmeans_small_launch(const KmeansArgs& p, int sms, cudaStream_t st) {
 }  // namespace spml
 
 #ifdef SPML_KM_TRACE
+extern "C" int spml_debug_kms_trace_all(long long* trace) {
+  return cudaMemcpyFromSymbol(trace, spml::g_kms_trace_all, sizeof(long long) * 160 * 16 * 16) ==
+                 cudaSuccess
+             ? 0 : -2;
+}
 extern "C" int spml_debug_kms_trace(long long* trace) {
   return cudaMemcpyFromSymbol(trace, spml::g_kms_trace, sizeof(long long) * 16 * 16) == cudaSuccess
              ? 0 : -2;

@@ -120,7 +120,7 @@ extern "C" {
 
 const char* spml_last_error(void) { return spml::g_error; }
 
-int spml_abi_version(void) { return 3; }
+int spml_abi_version(void) { return 4; }
 
 uint64_t spml_debug_launch_count(void) { return spml::g_launches.load(); }
 
