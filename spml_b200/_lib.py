@@ -86,6 +86,7 @@ SIGNATURES = {
     'spml_last_error': (ctypes.c_char_p, []),
     'spml_abi_version': (ctypes.c_int, []),
     'spml_debug_launch_count': (ctypes.c_uint64, []),
+    'spml_debug_kmeans_path': (ctypes.c_int, [c_i32, c_i32, c_i32, c_i32]),
     'spml_sizeof_struct': (c_sz, [ctypes.c_int]),
     'spml_normalize_rows_fwd': (ctypes.c_int, [c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp]),
     'spml_normalize_rows_bwd': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),

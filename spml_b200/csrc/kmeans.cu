@@ -334,18 +334,38 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
 //    (cp.async prefetch) fits, i.e. up to ~96 channels; the corner "many tiles per SM, D > 96"
 //    stays on the fp32 kernel, whose 2-4 co-resident CTAs per SM hide the per-tile latencies.
 // SPML_B200_KMEANS=fp32|tc|small overrides (read per call so that tests can compare them).
-enum KmeansPath { kPathFp32, kPathTc, kPathSmall };
+//  * SPML_B200_KMEANS=cluster: kmeans_cluster.cu, one thread-block cluster of up to 16 CTAs per
+//    image, everything in shared memory, no global traffic between the passes.  Same labels, but
+//    measured SLOWER than the small-K kernel at batch 1 (197 vs 94 us, VOC shape) and only 13 %
+//    faster at batch 4 (231 vs 266 us): 16 SMs per image are issue-bound in the argmax epilogue
+//    and the DSMEM exchange pays per 16-byte request (profiles/r2b_kmeans_cluster.md), so it is
+//    opt-in, not the default.
+enum KmeansPath { kPathFp32, kPathTc, kPathSmall, kPathCluster };
 
-static KmeansPath kmeans_path(int dim, int num_clusters, int batch, int64_t tiles, int sms) {
+static KmeansPath kmeans_path(int dim, int num_clusters, int batch, int max_rows, int64_t tiles,
+                              int sms) {
   const bool small_ok = spml::kmeans_small_supported(dim, num_clusters, batch, tiles * spml::BM);
   const bool tc_ok = spml::kmeans_tc_supported(dim);
   const char* e = getenv("SPML_B200_KMEANS");
+  const bool forced = e && *e;
   if (e && !strcmp(e, "fp32")) return kPathFp32;
   if (e && !strcmp(e, "tc") && tc_ok) return kPathTc;
   if (e && !strcmp(e, "small") && small_ok) return kPathSmall;
+  if (forced && !strcmp(e, "cluster") &&
+      spml::kmeans_cluster_supported(dim, num_clusters, batch, max_rows))
+    return kPathCluster;
   if (small_ok) return kPathSmall;
   if (!tc_ok) return kPathFp32;
   return (tiles <= sms || num_clusters >= 256 || dim <= 96) ? kPathTc : kPathFp32;
+}
+
+int spml_debug_kmeans_path(int batch, int max_rows_per_image, int dim, int num_clusters) {
+  int device = 0, sms = 0;
+  if (cudaGetDevice(&device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+    return -1;
+  return (int)kmeans_path(dim, num_clusters, batch, max_rows_per_image,
+                          (int64_t)batch * spml::ceil_div(max_rows_per_image, spml::BM), sms);
 }
 
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations) {
@@ -382,12 +402,13 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   int device = 0, sms = 0, per_sm = 0;
   SPML_CUDA(cudaGetDevice(&device));
   SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const KmeansPath path =
-      kmeans_path(dim, num_clusters, batch, (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
+  const KmeansPath path = kmeans_path(dim, num_clusters, batch, max_rows_per_image,
+                                      (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
   const bool use_tc = path == kPathTc;
   const int replicas = path == kPathTc ? kKmReplicas : 1;   // the small-K kernel pre-reduces per CTA
+  // (the cluster kernel keeps its sums in shared memory: only the poison flag is cleared)
   const size_t zeroed = kmeans_zeroed_bytes(batch, num_clusters, dim, iterations, replicas);
-  SPML_CUDA(cudaMemsetAsync(workspace, 0, zeroed, st));
+  SPML_CUDA(cudaMemsetAsync(workspace, 0, path == kPathCluster ? 16 : zeroed, st));
 
   KmeansArgs p{};
   p.x = x;
@@ -412,6 +433,7 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   p.labels_out64 = labels_out_i64;
   p.eps = 1e-12f;
 
+  if (path == kPathCluster) return kmeans_cluster_launch(p, max_rows_per_image, st);
   if (path == kPathSmall) return kmeans_small_launch(p, sms, st);
   const int64_t cap_rows = (int64_t)batch * max_rows_per_image;
   if (use_tc) {

@@ -69,6 +69,10 @@ constexpr int kKmReplicas = 2;   // copies of the segment sums in the tensor-cor
 bool kmeans_small_supported(int dim, int num_clusters, int batch, int64_t rows);
 int kmeans_small_launch(const KmeansArgs& p, int sms, cudaStream_t st);
 
+// kmeans_cluster.cu (an image fits in the shared memory of one thread-block cluster)
+bool kmeans_cluster_supported(int dim, int num_clusters, int batch, int max_rows);
+int kmeans_cluster_launch(const KmeansArgs& p, int max_rows, cudaStream_t st);
+
 // kmeans_tc.cu
 bool kmeans_tc_supported(int dim);
 size_t kmeans_tc_split_bytes(int batch, int num_clusters, int dim, int iterations);

@@ -89,7 +89,12 @@ def test_kmeans_matches_oracle(n, dim, k):
                                            (130, 16, 7, 1),
                                            # several tiles per CTA AND several prototype tiles per
                                            # pixel tile (two-stage ring, both prefetch paths)
-                                           (30000, 37, 300, 2), (25000, 66, 200, 1)])
+                                           (30000, 37, 300, 2), (25000, 66, 200, 1),
+                                           # one thread-block cluster per image (kmeans_cluster.cu):
+                                           # two accumulator rounds (K > 64), 5 channel slots,
+                                           # small clusters, an image with no rows
+                                           (16000, 37, 128, 1), (3000, 130, 40, 1), (2000, 66, 36, 2),
+                                           (16384, 66, 36, 1), (9, 66, 36, 4), (28000, 66, 64, 2)])
 def test_kmeans_tensor_core_equals_fp32(n, dim, k, batch, monkeypatch):
   """The tcgen05 E-step (with its exact re-check of near-ties) and the fp32 CUDA-core
   E-step return identical labels, also on data with no cluster structure (many near-ties)."""
@@ -102,7 +107,7 @@ def test_kmeans_tensor_core_equals_fp32(n, dim, k, batch, monkeypatch):
     per = (n + batch - 1) // batch
     img_off = torch.tensor([min(i * per, n) for i in range(batch + 1)], dtype=torch.int32).cuda()
     got = {}
-    paths = ('fp32', 'tc') + (('small',) if k <= 128 else ())   # 'small': kmeans_small.cu
+    paths = ('fp32', 'tc') + (('small', 'cluster') if k <= 128 else ())   # kmeans_small / _cluster.cu
     for path in paths:
       monkeypatch.setenv('SPML_B200_KMEANS', path)
       got[path], _ = ops.kmeans(e, img_off, batch, per, k, 10, lab0, want_i64=False)
@@ -570,7 +575,23 @@ def test_integration_snippet_runs():
         O.prototypes_from_labels(e, lab, 12))
 
 
-@pytest.mark.parametrize('path', ['small', 'tc', 'fp32'])
+def test_kmeans_cluster_path_is_taken(monkeypatch):
+  """With SPML_B200_KMEANS=cluster the shipped 512 x 512 shapes run the cluster kernel (so the
+  comparison above exercises it); larger maps and K > 128 fall back; it is never the default."""
+  from spml_b200 import _lib
+  lib = _lib.load()
+  assert lib.spml_debug_kmeans_path(1, 16384, 66, 36) == 2
+  monkeypatch.setenv('SPML_B200_KMEANS', 'cluster')
+  assert lib.spml_debug_kmeans_path(1, 16384, 66, 36) == 3
+  assert lib.spml_debug_kmeans_path(4, 16384, 66, 36) == 3
+  assert lib.spml_debug_kmeans_path(2, 16384, 66, 64) == 3
+  assert lib.spml_debug_kmeans_path(1, 16000, 37, 128) == 3
+  assert lib.spml_debug_kmeans_path(1, 3000, 130, 40) == 3
+  assert lib.spml_debug_kmeans_path(1, 37636, 66, 128) != 3
+  assert lib.spml_debug_kmeans_path(1, 16384, 66, 129) != 3
+
+
+@pytest.mark.parametrize('path', ['cluster', 'small', 'tc', 'fp32'])
 def test_kmeans_rejects_inputs_outside_the_fixed_point_range(path, monkeypatch):
   """the segment sums are 2^-32 fixed point (|x| <= 8); anything else used to give
   silently wrong labels.  Every kernel now flags it and the wrapper raises."""
