@@ -37,6 +37,17 @@ int segsort_bwd_impl(const spml_segsort_desc* d, const float* stats, const float
 int segsort_reduce_two(const float* pa, int ca, const float* pb, int cb, int64_t count, float* out,
                        cudaStream_t st);
 
+// normalize.cu: label packing + valid-pixel scan + normalise / pack in one launch (A8 front half)
+int scan_normalize_pack(const float* emb, const float* loc, int64_t loc_batch_stride, int loc_ch,
+                        const int64_t* labels, int has_ignore, int64_t ignore_index,
+                        const int64_t* ignore_dev, const int64_t* sem, const int64_t* inst,
+                        int64_t divisor, int64_t semantic_ignore, int64_t dropped,
+                        const int64_t* seeds, int64_t seed_batch_stride, int batch, int dim, int n,
+                        int64_t batch_index_offset, float eps, int32_t* dst, int32_t* img_off,
+                        float* e, float* el, float* nx, float* nc, int64_t* labels_out,
+                        int64_t* batch_out, int32_t* seed_out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st);
+
 #ifdef __CUDACC__
 // The loss of one problem from the per-tile partial sums of its row losses (loss.py:149-190
 // reduction; SPML_REDUCE_* in the header).  Executed by ONE warp; every lane gets the value.

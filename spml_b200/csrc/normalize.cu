@@ -24,8 +24,37 @@ __device__ __forceinline__ int64_t resolve_ignore(int64_t host_value, const int6
   return dev_value ? *dev_value : host_value;
 }
 
-// Single-pass chained scan (decoupled look-back) over tiles of kTile pixels.
-// state[t] packs {flag:32 | value:32}; flag 1 = tile aggregate, 2 = inclusive prefix.
+// Exclusive prefix of a tile's count over all tiles with a smaller ticket: every thread of
+// the CTA polls the aggregates of some of the preceding tiles (state[t] = {flag:32 | count:32},
+// published by publish_tile_count) and the CTA adds them up.  A FLAT look-back: the classic
+// decoupled look-back walks the chain tile by tile from one thread, ~0.1 us per tile, which
+// is 12 us for the 128 tiles of one 512 x 512 image; here a tile waits for the slowest of its
+// predecessors plus one L2 round trip.  Tiles take their number from a ticket, so every
+// predecessor is already running (or done) and publishes without waiting for anybody.
+__device__ __forceinline__ void publish_tile_count(unsigned long long* state, int tile, int total) {
+  // one 64-bit word: flag and count arrive together
+  reinterpret_cast<volatile unsigned long long*>(state)[tile] = (1ull << 32) | (unsigned)total;
+}
+__device__ __forceinline__ int tile_prefix(unsigned long long* state, int tile, int* s_red) {
+  volatile unsigned long long* vs = state;
+  int sum = 0;
+  for (int j = threadIdx.x; j < tile; j += blockDim.x) {
+    unsigned long long s;
+    do {
+      s = vs[j];
+    } while ((unsigned)(s >> 32) == 0);
+    sum += (int)(unsigned)(s & 0xffffffffu);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  int prefix = 0;
+  for (int w = 0; w < nwarps; ++w) prefix += s_red[w];
+  return prefix;
+}
+
 __global__ void valid_scan_kernel(const int64_t* __restrict__ labels, int has_ignore,
                                   int64_t ignore_host, const int64_t* __restrict__ ignore_dev,
                                   int batch, int n, int tiles_per_img,
@@ -34,7 +63,7 @@ __global__ void valid_scan_kernel(const int64_t* __restrict__ labels, int has_ig
                                   int* ticket) {
   __shared__ int s_tile;
   __shared__ int s_warp[kTile / 32];
-  __shared__ int s_prefix;
+  __shared__ int s_red[kTile / 32];
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
   __syncthreads();
   const int tile = s_tile;
@@ -53,62 +82,55 @@ __global__ void valid_scan_kernel(const int64_t* __restrict__ labels, int has_ig
     if (w < warp) before += s_warp[w];
     total += s_warp[w];
   }
+  if (threadIdx.x == 0) publish_tile_count(state, tile, total);
+  const int prefix = tile_prefix(state, tile, s_red);
   if (threadIdx.x == 0) {
-    int prefix = 0;
-    if (tile > 0) {
-      volatile unsigned long long* vs = state;
-      vs[tile] = (1ull << 32) | (unsigned)total;
-      int idx = tile - 1;
-      while (true) {
-        unsigned long long s = vs[idx];
-        const unsigned flag = (unsigned)(s >> 32);
-        if (flag == 0) continue;
-        prefix += (int)(unsigned)(s & 0xffffffffu);
-        if (flag == 2) break;
-        --idx;
-      }
-    }
-    __threadfence();
-    ((volatile unsigned long long*)state)[tile] = (2ull << 32) | (unsigned)(prefix + total);
-    s_prefix = prefix;
     if (tile % tiles_per_img == 0) img_off[b] = prefix;
     if (tile == batch * tiles_per_img - 1) img_off[batch] = prefix + total;
   }
-  __syncthreads();
   if (p < n) {
-    const int row = keep ? s_prefix + before + __popc(ballot & ((1u << lane) - 1)) : -1;
+    const int row = keep ? prefix + before + __popc(ballot & ((1u << lane) - 1)) : -1;
     dst[pix] = row;
     if (src && keep) src[row] = (int32_t)pix;
   }
 }
 
-// emb [batch, dim, n] -> e [rows, dim], el [rows, dim+loc_ch]
-__global__ void __launch_bounds__(kPackThreads)
-normalize_pack_fwd_kernel(const float* __restrict__ emb, const float* __restrict__ loc,
-                          int64_t loc_batch_stride, int loc_ch,
-                          const int64_t* __restrict__ labels, const int64_t* __restrict__ seeds,
-                          int64_t seed_batch_stride, const int32_t* __restrict__ dst, int dim,
-                          int n, int tiles_per_img, int64_t batch_index_offset, float eps,
-                          float* __restrict__ e, float* __restrict__ el, float* __restrict__ nx,
-                          float* __restrict__ nc, int64_t* __restrict__ labels_out,
-                          int64_t* __restrict__ batch_out, int32_t* __restrict__ seed_out) {
-  extern __shared__ float tile[];  // [dim][kTileLd]
-  __shared__ float s_nx[kTile], s_nc[kTile];
-  __shared__ int s_row[kTile];
-  const int b = blockIdx.x / tiles_per_img;
-  const int p0 = (blockIdx.x % tiles_per_img) * kTile;
-  const int np = min(kTile, n - p0);
+struct PackArgs {
+  const float* emb;          // [batch, dim, n]
+  const float* loc;          // [.., n, loc_ch]
+  int64_t loc_batch_stride;
+  int loc_ch;
+  const int64_t* seeds;
+  int64_t seed_batch_stride;
+  int dim, n, tiles_per_img;
+  int64_t batch_index_offset;
+  float eps;
+  float* e;                  // [rows, dim]
+  float* el;                 // [rows, dim + loc_ch]
+  float* nx;
+  float* nc;
+  int64_t* labels_out;
+  int64_t* batch_out;
+  int32_t* seed_out;
+};
+
+// the tile's embedding columns -> shared memory [dim][kTileLd] (coalesced along the pixels)
+__device__ __forceinline__ void pack_load_tile(const PackArgs& a, int b, int p0, int np, float* tile) {
   const int tid = threadIdx.x;
-  const int dp = dim + loc_ch;
+  const int px = tid % kTile;
+  for (int d = tid / kTile; d < a.dim; d += kPackThreads / kTile)
+    tile[d * kTileLd + px] = px < np ? a.emb[((int64_t)b * a.dim + d) * a.n + p0 + px] : 0.f;
+}
 
-  if (tid < kTile) s_row[tid] = tid < np ? dst[(int64_t)b * n + p0 + tid] : -1;
-  {
-    const int px = tid % kTile;
-    for (int d = tid / kTile; d < dim; d += kPackThreads / kTile)
-      tile[d * kTileLd + px] = px < np ? emb[((int64_t)b * dim + d) * n + p0 + px] : 0.f;
-  }
-  __syncthreads();
-
+// normalise the tile's pixels, concatenate the location channels, normalise again and write the
+// kept pixels to their rows (s_row[px], -1 = dropped); s_lab[px] = the pixel's label.  Needs a
+// __syncthreads() between pack_load_tile and this.
+__device__ __forceinline__ void pack_normalize_store(const PackArgs& a, int b, int p0, int np,
+                                                     float* tile, const int* s_row,
+                                                     const int64_t* s_lab, float* s_nx, float* s_nc) {
+  const int tid = threadIdx.x;
+  const int dim = a.dim, loc_ch = a.loc_ch, dp = dim + loc_ch;
+  const float eps = a.eps;
   if (tid < kTile) {
     float ss = 0.f;
     for (int d = 0; d < dim; ++d) {
@@ -125,7 +147,7 @@ normalize_pack_fwd_kernel(const float* __restrict__ emb, const float* __restrict
       ss2 += v * v;
     }
     if (tid < np) {
-      const float* lp = loc + (int64_t)b * loc_batch_stride + (int64_t)(p0 + tid) * loc_ch;
+      const float* lp = a.loc + (int64_t)b * a.loc_batch_stride + (int64_t)(p0 + tid) * loc_ch;
       for (int c = 0; c < loc_ch; ++c) ss2 += lp[c] * lp[c];
     }
     const float n2 = sqrtf(ss2);
@@ -141,21 +163,122 @@ normalize_pack_fwd_kernel(const float* __restrict__ emb, const float* __restrict
     const float div2 = fabsf(s_nc[px]);
     for (int d = lane; d < dim; d += 32) {
       const float v = tile[d * kTileLd + px];
-      e[(int64_t)r * dim + d] = v;
-      el[(int64_t)r * dp + d] = v / div2;
+      a.e[(int64_t)r * dim + d] = v;
+      a.el[(int64_t)r * dp + d] = v / div2;
     }
-    const int64_t pix = (int64_t)b * n + p0 + px;
     if (lane < loc_ch)
-      el[(int64_t)r * dp + dim + lane] =
-          loc[(int64_t)b * loc_batch_stride + (int64_t)(p0 + px) * loc_ch + lane] / div2;
+      a.el[(int64_t)r * dp + dim + lane] =
+          a.loc[(int64_t)b * a.loc_batch_stride + (int64_t)(p0 + px) * loc_ch + lane] / div2;
     if (lane == 0) {
-      nx[r] = s_nx[px];
-      nc[r] = s_nc[px];
-      if (labels_out) labels_out[r] = labels[pix];
-      if (batch_out) batch_out[r] = b + batch_index_offset;
-      if (seed_out) seed_out[r] = (int32_t)seeds[(int64_t)b * seed_batch_stride + p0 + px];
+      a.nx[r] = s_nx[px];
+      a.nc[r] = s_nc[px];
+      if (a.labels_out) a.labels_out[r] = s_lab[px];
+      if (a.batch_out) a.batch_out[r] = b + a.batch_index_offset;
+      if (a.seed_out) a.seed_out[r] = (int32_t)a.seeds[(int64_t)b * a.seed_batch_stride + p0 + px];
     }
   }
+}
+
+// emb [batch, dim, n] -> e [rows, dim], el [rows, dim+loc_ch]
+__global__ void __launch_bounds__(kPackThreads)
+normalize_pack_fwd_kernel(const PackArgs a, const int64_t* __restrict__ labels,
+                          const int32_t* __restrict__ dst) {
+  extern __shared__ float tile[];  // [dim][kTileLd]
+  __shared__ float s_nx[kTile], s_nc[kTile];
+  __shared__ int s_row[kTile];
+  __shared__ int64_t s_lab[kTile];
+  const int b = blockIdx.x / a.tiles_per_img;
+  const int p0 = (blockIdx.x % a.tiles_per_img) * kTile;
+  const int np = min(kTile, a.n - p0);
+  const int tid = threadIdx.x;
+  if (tid < kTile) {
+    s_row[tid] = tid < np ? dst[(int64_t)b * a.n + p0 + tid] : -1;
+    s_lab[tid] = (tid < np && a.labels_out) ? labels[(int64_t)b * a.n + p0 + tid] : 0;
+  }
+  pack_load_tile(a, b, p0, np, tile);
+  __syncthreads();
+  pack_normalize_store(a, b, p0, np, tile, s_row, s_lab, s_nx, s_nc);
+}
+
+// A8 front half in ONE kernel: label packing (sem * divisor + inst, ignored pixels dropped;
+// resnet_deeplab.py:118-137), the valid-pixel scan and the normalise / pack above.  The
+// embedding tile is requested before the CTA waits for the counts of the tiles in front of it,
+// so the scan costs no time of its own.  Replaces pack_labels_kernel + valid_scan_kernel +
+// normalize_pack_fwd_kernel (three dependent launches on the way to the k-means) in
+// spml_segment_by_kmeans.
+struct FusedLabelArgs {
+  const int64_t* labels;      // ready labels, or nullptr: sem * divisor + inst
+  int has_ignore;
+  int64_t ignore_host;
+  const int64_t* ignore_dev;
+  const int64_t* sem;
+  const int64_t* inst;
+  int64_t divisor, semantic_ignore, dropped;
+  int batch;
+  int32_t* dst;
+  int32_t* img_off;
+  unsigned long long* state;
+  int* ticket;
+};
+
+__global__ void __launch_bounds__(kPackThreads)
+scan_normalize_pack_kernel(const PackArgs a, const FusedLabelArgs f) {
+  extern __shared__ float tile[];  // [dim][kTileLd]
+  __shared__ float s_nx[kTile], s_nc[kTile];
+  __shared__ int s_row[kTile];
+  __shared__ int64_t s_lab[kTile];
+  __shared__ int s_tile;
+  __shared__ int s_warp[kTile / 32];
+  __shared__ int s_red[kPackThreads / 32];
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(f.ticket, 1);
+  __syncthreads();
+  const int t = s_tile;
+  const int b = t / a.tiles_per_img;
+  const int p0 = (t % a.tiles_per_img) * kTile;
+  const int np = min(kTile, a.n - p0);
+  bool keep = false;
+  unsigned ballot = 0;
+  if (tid < kTile) {   // whole warps
+    const int64_t pix = (int64_t)b * a.n + p0 + tid;
+    int64_t lab = 0;
+    if (tid < np) {
+      if (f.labels) {
+        const int64_t ignore_index = f.has_ignore ? resolve_ignore(f.ignore_host, f.ignore_dev) : 0;
+        lab = f.labels[pix];
+        keep = !f.has_ignore || (f.has_ignore == 2 ? lab < ignore_index : lab != ignore_index);
+      } else {
+        const int64_t sv = f.sem[pix];
+        lab = sv == f.semantic_ignore ? f.dropped : sv * f.divisor + f.inst[pix];
+        keep = lab != f.dropped;
+      }
+    }
+    s_lab[tid] = lab;
+    ballot = __ballot_sync(0xffffffffu, keep);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(ballot);
+  }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < kTile / 32; ++w) total += s_warp[w];
+  if (tid == 0) publish_tile_count(f.state, t, total);
+  pack_load_tile(a, b, p0, np, tile);              // in flight while the predecessors publish
+  const int prefix = tile_prefix(f.state, t, s_red);
+  if (tid == 0) {
+    if (t % a.tiles_per_img == 0) f.img_off[b] = prefix;
+    if (t == f.batch * a.tiles_per_img - 1) f.img_off[f.batch] = prefix + total;
+  }
+  if (tid < kTile) {
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w)
+      if (w < (tid >> 5)) before += s_warp[w];
+    const int row = keep ? prefix + before + __popc(ballot & ((1u << (tid & 31)) - 1)) : -1;
+    s_row[tid] = row;
+    if (tid < np) f.dst[(int64_t)b * a.n + p0 + tid] = row;
+  }
+  __syncthreads();
+  pack_normalize_store(a, b, p0, np, tile, s_row, s_lab, s_nx, s_nc);
 }
 
 constexpr int kMaxPerLane = (SPML_MAX_DIM + 31) / 32;  // channel slots per lane
@@ -232,6 +355,45 @@ static int tiles_per_image(int n) { return (int)ceil_div(n, kTile); }
 
 }  // namespace spml
 
+namespace spml {
+
+// pipeline.cu: labels (or sem / inst) -> dst, img_off, packed rows in one launch
+int scan_normalize_pack(const float* emb, const float* loc, int64_t loc_batch_stride, int loc_ch,
+                        const int64_t* labels, int has_ignore, int64_t ignore_index,
+                        const int64_t* ignore_dev, const int64_t* sem, const int64_t* inst,
+                        int64_t divisor, int64_t semantic_ignore, int64_t dropped,
+                        const int64_t* seeds, int64_t seed_batch_stride, int batch, int dim, int n,
+                        int64_t batch_index_offset, float eps, int32_t* dst, int32_t* img_off,
+                        float* e, float* el, float* nx, float* nc, int64_t* labels_out,
+                        int64_t* batch_out, int32_t* seed_out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+  SPML_CHECK_SUPPORTED(loc_ch >= 0 && loc_ch <= 32 && dim + loc_ch <= SPML_MAX_DIM,
+                       "normalize_pack_fwd: dim %d + loc_ch %d exceeds %d", dim, loc_ch,
+                       SPML_MAX_DIM);
+  SPML_CHECK_SUPPORTED((int64_t)batch * n < (1ll << 31), "valid_scan: more than 2^31 pixels");
+  const size_t need = spml_valid_scan_workspace_bytes(batch, n);
+  if (workspace_bytes < need) {
+    set_error("valid_scan: workspace %zu < %zu bytes", workspace_bytes, need);
+    return SPML_E_WORKSPACE;
+  }
+  SPML_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  const int tpi = tiles_per_image(n);
+  PackArgs pa{emb, loc, loc_batch_stride, loc_ch, seeds, seed_batch_stride, dim, n, tpi,
+              batch_index_offset, eps, e, el, nx, nc, labels_out, batch_out, seed_out};
+  FusedLabelArgs fa{labels, has_ignore, ignore_index, ignore_dev, sem, inst, divisor,
+                    semantic_ignore, dropped, batch, dst, img_off,
+                    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16),
+                    reinterpret_cast<int*>(workspace)};
+  const size_t smem = (size_t)dim * kTileLd * sizeof(float);
+  SPML_CUDA(cudaFuncSetAttribute(scan_normalize_pack_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_normalize_pack_kernel<<<batch * tpi, kPackThreads, smem, st>>>(pa, fa);
+  SPML_LAUNCH_CHECK("scan_normalize_pack_kernel");
+  return SPML_OK;
+}
+
+}  // namespace spml
+
 extern "C" {
 
 size_t spml_valid_scan_workspace_bytes(int batch, int n) {
@@ -283,10 +445,10 @@ int spml_normalize_pack_fwd(const float* emb, const float* loc, int64_t loc_batc
   SPML_CUDA(cudaFuncSetAttribute(spml::normalize_pack_fwd_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tpi = spml::tiles_per_image(n);
+  spml::PackArgs pa{emb, loc, loc_batch_stride, loc_ch, seeds, seed_batch_stride, dim, n, tpi,
+                    batch_index_offset, eps, e, el, nx, nc, labels_out, batch_out, seed_out};
   spml::normalize_pack_fwd_kernel<<<batch * tpi, spml::kPackThreads, smem,
-                                    spml::as_stream(stream)>>>(
-      emb, loc, loc_batch_stride, loc_ch, labels, seeds, seed_batch_stride, dst, dim, n, tpi,
-      batch_index_offset, eps, e, el, nx, nc, labels_out, batch_out, seed_out);
+                                    spml::as_stream(stream)>>>(pa, labels, dst);
   SPML_LAUNCH_CHECK("normalize_pack_fwd_kernel");
   return SPML_OK;
 }

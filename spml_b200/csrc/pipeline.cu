@@ -558,26 +558,40 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
   int64_t* packed = c.take<int64_t>((size_t)cap);
   cudaStream_t st = as_stream(stream);
 
-  const int64_t* labels = a->labels;
-  int has_ignore = a->has_ignore;
-  int64_t ignore_index = a->ignore_index;
-  const int64_t* ignore_dev = a->ignore_index_dev;
-  if (!labels) {
-    pack_labels_kernel<<<blocks_of(cap), 256, 0, st>>>(a->sem, a->inst, cap, a->label_divisor,
-                                                      a->semantic_ignore, packed);
-    SPML_LAUNCH_CHECK("pack_labels_kernel");
-    labels = packed;
-    has_ignore = 1;
-    ignore_index = kDroppedLabel;
-    ignore_dev = nullptr;
+  // label packing (sem * divisor + inst, ignored pixels dropped) + valid-pixel scan + normalise /
+  // pack: one kernel (normalize.cu::scan_normalize_pack_kernel)
+  static const bool fused_prepass = []() {
+    const char* e = getenv("SPML_B200_FUSED_PREPASS");   // =0: the three round-1 kernels (A/B timing)
+    return !(e && e[0] == '0');
+  }();
+  if (fused_prepass) {
+  SPML_TRY(scan_normalize_pack(a->emb, a->loc, a->loc_batch_stride, a->loc_ch, a->labels,
+                               a->has_ignore, a->ignore_index, a->ignore_index_dev, a->sem, a->inst,
+                               a->label_divisor, a->semantic_ignore, kDroppedLabel, a->seeds,
+                               a->seed_batch_stride, a->batch, a->dim, a->n, a->batch_index_offset,
+                               a->eps, a->dst, a->img_off, a->e, a->el, a->nx, a->nc, a->labels_out,
+                               a->batch_out, a->seed_out, scan_ws, scan_bytes, st));
+  } else {
+    const int64_t* labels = a->labels;
+    int has_ignore = a->has_ignore;
+    int64_t ignore_index = a->ignore_index;
+    const int64_t* ignore_dev = a->ignore_index_dev;
+    if (!labels) {
+      pack_labels_kernel<<<blocks_of(cap), 256, 0, st>>>(a->sem, a->inst, cap, a->label_divisor,
+                                                        a->semantic_ignore, packed);
+      SPML_LAUNCH_CHECK("pack_labels_kernel");
+      labels = packed;
+      has_ignore = 1;
+      ignore_index = kDroppedLabel;
+      ignore_dev = nullptr;
+    }
+    SPML_TRY(spml_valid_scan(labels, has_ignore, ignore_index, ignore_dev, a->batch, a->n, a->dst,
+                             nullptr, a->img_off, scan_ws, scan_bytes, stream));
+    SPML_TRY(spml_normalize_pack_fwd(a->emb, a->loc, a->loc_batch_stride, a->loc_ch, labels,
+                                     a->seeds, a->seed_batch_stride, a->dst, a->batch, a->dim, a->n,
+                                     a->batch_index_offset, a->eps, a->e, a->el, a->nx, a->nc,
+                                     a->labels_out, a->batch_out, a->seed_out, stream));
   }
-  SPML_TRY(spml_valid_scan(labels, has_ignore, ignore_index, ignore_dev,
-                           a->batch, a->n, a->dst, nullptr, a->img_off, scan_ws, scan_bytes,
-                           stream));
-  SPML_TRY(spml_normalize_pack_fwd(a->emb, a->loc, a->loc_batch_stride, a->loc_ch, labels,
-                                   a->seeds, a->seed_batch_stride, a->dst, a->batch, a->dim, a->n,
-                                   a->batch_index_offset, a->eps, a->e, a->el, a->nx, a->nc,
-                                   a->labels_out, a->batch_out, a->seed_out, stream));
   SPML_TRY(spml_kmeans(a->el, a->img_off, a->batch, a->n, dl, a->num_clusters, a->k_per_image,
                        a->iterations, a->seed_out, a->kmeans_labels, nullptr, km_ws, km_bytes,
                        stream));
