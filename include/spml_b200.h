@@ -49,7 +49,7 @@ int spml_abi_version(void);
  * was loaded (memsets are not counted). */
 uint64_t spml_debug_launch_count(void);
 /* diagnostics: which k-means kernel spml_kmeans runs for this shape on the current device
- * (0 fp32 CUDA cores, 1 tcgen05 tiles, 2 tcgen05 small-K, 3 one thread-block cluster per image: opt-in). */
+ * (0 fp32 CUDA cores, 1 tcgen05 tiles, 2 tcgen05 small-K, 3 one thread-block cluster per image). */
 int spml_debug_kmeans_path(int batch, int max_rows_per_image, int dim, int num_clusters);
 /* sizeof the argument structs below (0: spml_segsort_desc, 1: spml_cluster_args, 2:
  * spml_head_args), so that a binding can check its own struct layout at load time. */

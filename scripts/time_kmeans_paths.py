@@ -19,13 +19,18 @@ def clustering_input(w, step=0):
   off = torch.arange(B + 1, dtype=torch.int32, device='cuda') * (H * W)
   return el, off, B, H * W, w.num_clusters[0] * w.num_clusters[1], lab0
 
+import dataclasses
 for name in (sys.argv[1:] or ['voc_scribble_b1', 'voc_scribble_b4', 'voc_tag_b2']):
-  w = synth.WORKLOADS[name]
+  # NAME or NAME@BATCH (the workload at another batch size)
+  base, _, nb = name.partition('@')
+  w = synth.WORKLOADS[base]
+  if nb:
+    w = dataclasses.replace(w, batch=int(nb))
   el, off, B, n, K, lab0 = clustering_input(w)
   lib = _lib.load()
   print(name, 'default path:', lib.spml_debug_kmeans_path(B, n, el.shape[1], K))
   got = {}
-  for path in ('cluster', 'small', 'tc', 'fp32'):
+  for path in ('cluster', 'small', 'fp32'):
     os.environ['SPML_B200_KMEANS'] = path
     for _ in range(5):
       out, _ = ops.kmeans(el, off, B, n, K, w.iterations, lab0, want_i64=False)
@@ -40,6 +45,6 @@ for name in (sys.argv[1:] or ['voc_scribble_b1', 'voc_scribble_b4', 'voc_tag_b2'
     got[path] = out.clone()
     print('  %-8s %8.1f us / call   %s' % (path, ev[0].elapsed_time(ev[1]) * 1e3 / reps,
           'labels == fp32: %s' % bool(torch.equal(out, got.get('fp32', out))) if path == 'fp32' else ''))
-  for path in ('cluster', 'small', 'tc'):
+  for path in ('cluster', 'small'):
     print('  %s == fp32: %s (%d differ)' % (path, bool(torch.equal(got[path], got['fp32'])),
                                           int((got[path] != got['fp32']).sum())))

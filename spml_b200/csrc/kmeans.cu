@@ -334,12 +334,14 @@ static size_t kmeans_split_offset(int batch, int num_clusters, int dim, int iter
 //    (cp.async prefetch) fits, i.e. up to ~96 channels; the corner "many tiles per SM, D > 96"
 //    stays on the fp32 kernel, whose 2-4 co-resident CTAs per SM hide the per-tile latencies.
 // SPML_B200_KMEANS=fp32|tc|small overrides (read per call so that tests can compare them).
-//  * SPML_B200_KMEANS=cluster: kmeans_cluster.cu, one thread-block cluster of up to 16 CTAs per
-//    image, everything in shared memory, no global traffic between the passes.  Same labels, but
-//    measured SLOWER than the small-K kernel at batch 1 (197 vs 94 us, VOC shape) and only 13 %
-//    faster at batch 4 (231 vs 266 us): 16 SMs per image are issue-bound in the argmax epilogue
-//    and the DSMEM exchange pays per 16-byte request (profiles/r2b_kmeans_cluster.md), so it is
-//    opt-in, not the default.
+//  * kmeans_cluster.cu: one thread-block cluster of up to 16 CTAs per image, everything in shared
+//    memory, no global traffic between the passes.  Its time hardly depends on the batch (images
+//    are independent clusters), while the small-K kernel serialises the tiles of a CTA.  Measured
+//    (VOC shape, K = 36, us per call, profiles/r2b_kmeans_paths.txt): batch 1: 197 vs 94 (16 SMs
+//    per image are issue-bound in the argmax epilogue and the DSMEM exchange pays per 16-byte
+//    request), batch 2: 232 vs 161, batch 3: 231 vs 212, batch 4: 231 vs 266, batch 8: 404 vs 456,
+//    batch 16: 636 vs 959; with K = 64 the two are level up to batch 8.  Default from batch 4 on
+//    when K <= 48; SPML_B200_KMEANS=cluster forces it wherever it fits.
 enum KmeansPath { kPathFp32, kPathTc, kPathSmall, kPathCluster };
 
 static KmeansPath kmeans_path(int dim, int num_clusters, int batch, int max_rows, int64_t tiles,
@@ -351,7 +353,7 @@ static KmeansPath kmeans_path(int dim, int num_clusters, int batch, int max_rows
   if (e && !strcmp(e, "fp32")) return kPathFp32;
   if (e && !strcmp(e, "tc") && tc_ok) return kPathTc;
   if (e && !strcmp(e, "small") && small_ok) return kPathSmall;
-  if (forced && !strcmp(e, "cluster") &&
+  if (((forced && !strcmp(e, "cluster")) || (!forced && batch >= 4 && num_clusters <= 48)) &&
       spml::kmeans_cluster_supported(dim, num_clusters, batch, max_rows))
     return kPathCluster;
   if (small_ok) return kPathSmall;

@@ -7,7 +7,10 @@
 
 namespace spml {
 
-constexpr int kTile = 128;          // pixels per CTA (also the scan granularity)
+#ifndef SPML_PACK_TILE
+#define SPML_PACK_TILE 64
+#endif
+constexpr int kTile = SPML_PACK_TILE;   // pixels per CTA (also the scan granularity)
 constexpr int kTileLd = kTile + 1;  // odd stride: conflict-free in both directions
 constexpr int kPackThreads = 256;
 

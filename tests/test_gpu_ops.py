@@ -577,10 +577,14 @@ def test_integration_snippet_runs():
 
 def test_kmeans_cluster_path_is_taken(monkeypatch):
   """With SPML_B200_KMEANS=cluster the shipped 512 x 512 shapes run the cluster kernel (so the
-  comparison above exercises it); larger maps and K > 128 fall back; it is never the default."""
+  comparison above exercises it); larger maps and K > 128 fall back.  By default it runs from
+  batch 4 on (where it is measured faster than the small-K kernel)."""
   from spml_b200 import _lib
   lib = _lib.load()
+  monkeypatch.delenv('SPML_B200_KMEANS', raising=False)
   assert lib.spml_debug_kmeans_path(1, 16384, 66, 36) == 2
+  assert lib.spml_debug_kmeans_path(4, 16384, 66, 36) == 3
+  assert lib.spml_debug_kmeans_path(4, 16384, 66, 64) == 2
   monkeypatch.setenv('SPML_B200_KMEANS', 'cluster')
   assert lib.spml_debug_kmeans_path(1, 16384, 66, 36) == 3
   assert lib.spml_debug_kmeans_path(4, 16384, 66, 36) == 3
