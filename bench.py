@@ -63,6 +63,10 @@ def parse_args():
                   help='train_* workloads: autocast dtype of the cuDNN backbone')
   ap.add_argument('--no-graph', action='store_true',
                   help='launch the kernels directly instead of replaying the CUDA graph (for ncu)')
+  ap.add_argument('--no-train-arm', action='store_true',
+                  help='contrastive-step workloads: skip the secondary training-step measurement '
+                       '(ResNet-101 backbone + head + one NCCL all-reduce) reported under '
+                       '"training_step"')
   return ap.parse_args()
 
 
@@ -535,7 +539,7 @@ def run_b200(args):
     roofline = dict(per_kernel[top])
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (a profiler
     # number cannot be taken inside a timed run); null when this workload was not captured
-    for tname in ('r2_traffic.json', 'r1c_traffic.json'):
+    for tname in ('r2b_traffic.json', 'r2_traffic.json', 'r1c_traffic.json'):
       tpath = os.path.join(ROOT, 'profiles', tname)
       if os.path.exists(tpath):
         traffic = json.load(open(tpath))
@@ -580,9 +584,41 @@ def run_b200(args):
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'breakdown': breakdown,
     }
-    print(json.dumps(line))
+  else:
+    line = None
   if world > 1:
     dist.destroy_process_group()
+  return line
+
+
+def training_step_arm(args):
+  """BASELINE.json's metric has two clauses; the line above is the second (contrastive-loss
+  step).  The first - training images/s with the ResNet-101 backbone and ONE NCCL all-reduce of
+  the gradients at 1/2/4/8 GPUs - is the `train_voc_b4` workload of this script; it is run here
+  as well (every rank starts the same command on its own rendezvous port, after this process has
+  left its process group) so that the default invocation reports both.  Never fails the line."""
+  import subprocess
+  # (torchrun's agent serves the rendezvous store of THIS process group only: without its
+  # variables rank 0 of the second command hosts its own store on the other port)
+  env = {k: v for k, v in os.environ.items() if not k.startswith('TORCHELASTIC')}
+  if 'MASTER_PORT' in env:
+    env['MASTER_PORT'] = str(1024 + (int(env['MASTER_PORT']) + 4321 - 1024) % 60000)
+  cmd = [sys.executable, os.path.abspath(__file__), '--workload', 'train_voc_b4', '--gpus',
+         str(args.gpus), '--steps', '10', '--warmup', '3']
+  try:
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
+    rows = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    if not rows:
+      return {'error': (out.stderr or 'no output')[-300:]}
+    t = json.loads(rows[-1])
+    return {'metric': t['metric'], 'value': t['value'], 'unit': t['unit'], 'n_gpus': t['n_gpus'],
+            'ms_per_step': t['ms_per_step'], 'steps': t['steps'], 'warmup': t['warmup'],
+            'scaling': t['scaling'], 'dtype': t['dtype'], 'config': t['config'],
+            'phase_ms': t['phase_ms'], 'all_reduce': t['all_reduce'],
+            'contrastive_head_ms': t['contrastive_head_ms'], 'clocks': t['clocks'],
+            'command': 'bench.py --workload train_voc_b4 --gpus %d --steps 10 --warmup 3' % args.gpus}
+  except Exception as e:   # noqa: BLE001 (a secondary figure must not cost the headline)
+    return {'error': repr(e)[-300:]}
 
 
 # ------------------------------------------------------------------------------ training step
@@ -812,7 +848,14 @@ def main():
   elif args.impl == 'reference':
     run_reference(args)
   else:
-    run_b200(args)
+    line = run_b200(args)
+    train = None
+    if not args.no_train_arm and args.workload == 'voc_scribble_b1':
+      train = training_step_arm(args)       # every rank takes part; rank 0 keeps the result
+    if line is not None:
+      if train is not None:
+        line['training_step'] = train
+      print(json.dumps(line))
 
 
 if __name__ == '__main__':

@@ -6,7 +6,7 @@ TAG=${1:-r2b}
 O=gpurun_out
 mkdir -p $O
 for W in voc_scribble_b1 voc_scribble_b4 voc_tag_b2 densepose_b1 voc_scribble_softmax_b1; do
-  timeout 600 python bench.py --workload $W > $O/${TAG}_bench_$W.json 2> $O/${TAG}_bench_$W.err
+  timeout 600 python bench.py --no-train-arm --workload $W > $O/${TAG}_bench_$W.json 2> $O/${TAG}_bench_$W.err
 done
 timeout 900 python bench.py --impl reference > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err
 timeout 900 python bench.py --workload train_voc_b4 > $O/${TAG}_train_voc_b4_1gpu.json 2> $O/${TAG}_train_voc_b4_1gpu.err
