@@ -39,6 +39,11 @@ for it in range(1, w.iterations + 1):
   total = prev - r[:, 0]
   parts.append('| pass %d/%d' % (int(total.median()), int(total.max())))
   parts.append('| all MMAs issued %d after barrier B' % int((r[:, 8] - r[:, 4]).median()))
+  own = r[r[:, 9] > r[:, 2]]
+  if own.numel():
+    parts.append('| rebuild (warp 0 of the owners that had work): gathered +%d, normalised +%d, operand rows sent +%d'
+                 % (int((own[:, 9] - own[:, 2]).median()), int((own[:, 10] - own[:, 9]).median()),
+                    int((own[:, 3] - own[:, 10]).median())))
   parts.append('| ambiguous rows %d (max %d per CTA), changed rows %d' %
                (int(r[:, 14].sum()), int(r[:, 14].max()), int(r[:, 15].sum())))
   print('it %2d  %s' % (it, '  '.join(parts)))

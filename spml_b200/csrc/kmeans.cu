@@ -404,8 +404,11 @@ int spml_kmeans(const float* x, const int32_t* img_off, int batch, int max_rows_
   int device = 0, sms = 0, per_sm = 0;
   SPML_CUDA(cudaGetDevice(&device));
   SPML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const KmeansPath path = kmeans_path(dim, num_clusters, batch, max_rows_per_image,
-                                      (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
+  KmeansPath path = kmeans_path(dim, num_clusters, batch, max_rows_per_image,
+                                (int64_t)batch * ceil_div(max_rows_per_image, BM), sms);
+  // (the cluster kernel keeps the fp32 prototypes of a pass in the prototype scratch, padded to
+  // 16-byte blocks: the scratch of a single iteration has no room for the padding)
+  if (path == kPathCluster && iterations < 2) path = kPathSmall;
   const bool use_tc = path == kPathTc;
   const int replicas = path == kPathTc ? kKmReplicas : 1;   // the small-K kernel pre-reduces per CTA
   // (the cluster kernel keeps its sums in shared memory: only the poison flag is cleared)

@@ -40,7 +40,8 @@ constexpr int kKcThreads = 512;
 constexpr int kKcWarps = kKcThreads / 32;
 constexpr int kKcMaxCluster = 16;
 constexpr int kKcMaxTiles = 8;        // pixel tiles per CTA: 8 accumulators of 64 columns = TMEM
-constexpr int kKcAmbCap = 256;        // ambiguous rows per CTA and pass settled by candidate pairs
+constexpr int kKcAmbCap = 192;        // ambiguous rows per CTA and pass settled by candidate pairs
+constexpr int kKcStage = 40;          // ... of which the first ones have their fp32 row staged in shared memory
 constexpr int kKcCand = 4;            // candidates per ambiguous row (more: warp-per-row path)
 constexpr int kKcSmemLimit = 227 * 1024;
 
@@ -73,7 +74,7 @@ struct KmeansClusterArgs {
 
 // byte offsets of the dynamic shared memory (from a 128-byte aligned base)
 struct KcLayout {
-  uint32_t a, b, hi, lo, tot, hst, amb, pk, sc, lab, old, total;
+  uint32_t a, b, hi, lo, tot, hst, pf, xst, amb, pk, sc, lab, old, total;
 };
 __host__ __device__ inline uint32_t kc_up(uint32_t x, uint32_t al) { return (x + al - 1) / al * al; }
 __host__ __device__ inline KcLayout kc_layout(int K, int dim, int kp, int bn, int max_tiles, int own) {
@@ -84,7 +85,9 @@ __host__ __device__ inline KcLayout kc_layout(int K, int dim, int kp, int bn, in
   L.hi = o, o += (uint32_t)K * dim * 4;                    // this CTA's contribution, high halves
   L.lo = o, o = kc_up(o + (uint32_t)K * dim * 4, 16);
   L.tot = o, o = kc_up(o + (uint32_t)own * dim * 8, 16);   // running totals of the owned prototypes
-  L.hst = o, o += (uint32_t)own * kp * 2;                  // the owned prototypes as fp16 operand rows (staging)
+  L.hst = o, o = kc_up(o + (uint32_t)own * kp * 2, 16);    // the owned prototypes as fp16 operand rows (staging)
+  L.pf = o, o += kc_up((uint32_t)K * dim, 4) * 4;          // fp32 prototypes of the pass (copy of the scratch)
+  L.xst = o, o = kc_up(o + (uint32_t)kKcStage * dim * 4, 16);    // fp32 rows of the first ambiguous rows
   const uint32_t need_a = kKcAmbCap * (1 + 2 * kKcCand), need_c = (uint32_t)max_tiles * BM;
   const uint32_t lists = need_a > need_c ? need_a : need_c;
   L.amb = o;                                               // ambiguous rows | changed rows (later)
@@ -111,16 +114,55 @@ __host__ __device__ constexpr uint32_t kc_idesc_f16(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void kc_cp_async_16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void kc_cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void kc_cp_async_4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+}
+// one fp32 row global -> shared, asynchronously, by ONE thread (a row that has just turned out
+// ambiguous: its values are needed by the exact re-check after the E-step)
+__device__ __forceinline__ void kc_stage_row(float* dst, const float* src, int dim) {
+  if ((dim & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+    for (int d = 0; d < dim; d += 2) kc_cp_async_8(dst + d, src + d);
+  } else {
+    for (int d = 0; d < dim; ++d) kc_cp_async_4(dst + d, src + d);
+  }
+}
+// the fmaf chain of the fp32 kernel (d ascending from 0) on two rows in shared memory
+__device__ __forceinline__ float kc_chain_shared(const float* __restrict__ xr,
+                                                 const float* __restrict__ pr, int dim) {
+  float acc = 0.f;
+  int d = 0;
+  if ((dim & 1) == 0 && ((tc::smem_u32(xr) | tc::smem_u32(pr)) & 7u) == 0) {
+#pragma unroll 2
+    for (; d + 8 <= dim; d += 8) {
+      float2 xv[4], pv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float2*>(xr + d + 2 * j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pv[j] = *reinterpret_cast<const float2*>(pr + d + 2 * j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc = fmaf(xv[j].x, pv[j].x, acc);
+        acc = fmaf(xv[j].y, pv[j].y, acc);
+      }
+    }
+  }
+  for (; d < dim; ++d) acc = fmaf(xr[d], pr[d], acc);
+  return acc;
+}
 __device__ __forceinline__ void kc_prefetch_row(const float* row, int dim) {
   const char* p0 = reinterpret_cast<const char*>(row);
   for (int o = 0; o < dim * 4 + 127; o += 128)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + min(o, dim * 4 - 4)) : "memory");
 }
 
-// the fp32 score of the fp32 kernel: acc = fmaf(x[d], p[d], acc), d ascending from 0.  xr is a
-// row in global memory that was prefetched into L1 when the row turned out ambiguous, pr a
-// prototype row in the shared memory of its owner (possibly another CTA of the cluster, ~200
-// cycles away): the whole prototype row is requested before the chain starts.
+// the fp32 score of the fp32 kernel: acc = fmaf(x[d], p[d], acc), d ascending from 0, for the
+// rare warp-per-row path: xr is a row in global memory, pr a prototype row in shared memory.
 template <int kSlots>
 __device__ __forceinline__ float kc_exact_score(const float* __restrict__ xr,
                                                 const float* __restrict__ pr, int dim) {
@@ -131,7 +173,7 @@ __device__ __forceinline__ float kc_exact_score(const float* __restrict__ xr,
     for (int h0 = 0; h0 < n2; h0 += kH) {
       float2 pv[kH];
 #pragma unroll
-      for (int c = 0; c < kH; ++c) pv[c] = __ldca(reinterpret_cast<const float2*>(pr) + min(h0 + c, n2 - 1));
+      for (int c = 0; c < kH; ++c) pv[c] = reinterpret_cast<const float2*>(pr)[min(h0 + c, n2 - 1)];
 #pragma unroll
       for (int c0 = 0; c0 < kH; c0 += 8) {
         if (h0 + c0 < n2) {
@@ -150,7 +192,7 @@ __device__ __forceinline__ float kc_exact_score(const float* __restrict__ xr,
     }
     return acc;
   }
-  for (int d = 0; d < dim; ++d) acc = fmaf(__ldca(xr + d), __ldca(pr + d), acc);
+  for (int d = 0; d < dim; ++d) acc = fmaf(__ldca(xr + d), pr[d], acc);
   return acc;
 }
 
@@ -189,7 +231,10 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
   const int kb = p.k_per_image ? p.k_per_image[b] : K;
   const float* __restrict__ x = p.x + row_lo * dim;
   // fp32 prototypes of the image (workspace): written by their owners, read by the re-checks
-  float* gpf = p.protos + (size_t)b * K * dim;
+  // (16-byte aligned blocks: they are copied into shared memory with 16-byte cp.async)
+  const int pf_stride = (K * dim + 3) & ~3;
+  float* gpf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.protos) + 15) & ~uintptr_t(15)) +
+               (size_t)b * pf_stride;
 
   uint8_t* smem = kc_smem_raw + ((128u - (tc::smem_u32(kc_smem_raw) & 127u)) & 127u);
   const KcLayout L = kc_layout(K, dim, kp, bn, a.max_tiles, a.own);
@@ -199,6 +244,8 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
   int* s_lo = reinterpret_cast<int*>(smem + L.lo);
   long long* s_tot = reinterpret_cast<long long*>(smem + L.tot);
   __half* s_hst = reinterpret_cast<__half*>(smem + L.hst);
+  float* pf = reinterpret_cast<float*>(smem + L.pf);          // [K][dim]
+  float* s_xst = reinterpret_cast<float*>(smem + L.xst);      // [kKcStage][dim]
   uint32_t* s_amb = reinterpret_cast<uint32_t*>(smem + L.amb);   // row | candidates << 16
   int* s_pk = reinterpret_cast<int*>(smem + L.pk);               // [slot][kKcCand] prototype index
   float* s_sc = reinterpret_cast<float*>(smem + L.sc);           // [slot][kKcCand] exact score
@@ -374,6 +421,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
 #pragma unroll
           for (int s = 0; s < kSlots; ++s) delta[s] += (long long)rh[q][s] * 65536ll + rl[q][s];
       }
+      KCT(9);
       float v[kSlots];
       float ss = 0.f;
 #pragma unroll
@@ -403,6 +451,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
         }
       }
       __syncwarp();
+      KCT(10);
       // the fp16 operand row into every CTA of the cluster, 16 bytes (one core-matrix row) a store
       for (int idx = lane; idx < cs * nchunk; idx += 32) {
         const int dst = idx / nchunk, c = idx - dst * nchunk;
@@ -415,6 +464,9 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
     KCT(3);
     cluster.sync();   // the operand rows of every owner have arrived
     KCT(4);
+    // the fp32 prototypes of this pass (written by their owners in front of the barrier) into
+    // shared memory, behind the MMAs and the epilogue: nobody needs them before the re-check
+    for (int i = tid; i < pf_stride / 4; i += kKcThreads) kc_cp_async_16(pf + 4 * i, gpf + 4 * i);
     for (int i = tid; i < per_img; i += kKcThreads) s_hi[i] = 0, s_lo[i] = 0;
     for (int i = tid; i < (nrows + 3) / 4; i += kKcThreads)
       reinterpret_cast<uint32_t*>(s_old)[i] = reinterpret_cast<const uint32_t*>(s_lab)[i];
@@ -479,13 +531,15 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
         const bool amb = valid && !(b1 - b2 >= tau);   // also catches NaN
         if (valid) s_lab[rloc] = (uint8_t)k1;
         // the fp32 row of a row that is ambiguous or moves is needed in a moment: into L1
-        if (amb || (valid && it < T && k1 != (int)s_old[rloc])) kc_prefetch_row(x + (int64_t)rloc * dim, dim);
+        if (valid && !amb && it < T && k1 != (int)s_old[rloc]) kc_prefetch_row(x + (int64_t)rloc * dim, dim);
         if (__any_sync(0xffffffffu, amb)) {
           // ---- the candidates of an ambiguous row: every prototype within tau of the best
           int slot = -1, cnt = 0;
           if (amb) {
             slot = atomicAdd(&s_namb, 1);
             if (slot >= kKcAmbCap) slot = -1;
+            if (slot >= 0 && slot < kKcStage) kc_stage_row(s_xst + slot * dim, x + (int64_t)rloc * dim, dim);
+            else kc_prefetch_row(x + (int64_t)rloc * dim, dim);
           }
           const float thr = b1 - tau;
           for (int cb = 0; cb < kb; cb += 32) {
@@ -501,10 +555,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
                   for (int u = u0; u < u0 + 4; ++u) {
                     const float sc = __uint_as_float(v[u]);
                     if (u < live && (sc >= thr || sc != sc)) {
-                      if (cnt < kKcCand) {
-                        s_pk[slot * kKcCand + cnt] = cb + u;
-                        kc_prefetch_row(gpf + (cb + u) * dim, dim);
-                      }
+                      if (cnt < kKcCand) s_pk[slot * kKcCand + cnt] = cb + u;
                       ++cnt;
                     }
                   }
@@ -521,6 +572,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
           }
         }
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");   // fp32 prototypes, rows of the ambiguous rows
       tc::tcgen05_fence_before();
       __syncthreads();   // the accumulators are free for the next round
     }
@@ -535,7 +587,9 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
         const int cnt = (int)(rec >> 16), c = i % kKcCand;
         if (cnt <= kKcCand && c < cnt) {
           const int k = s_pk[i];
-          s_sc[i] = kc_exact_score<kSlots>(x + (int64_t)(rec & 0xffffu) * dim, gpf + k * dim, dim);
+          s_sc[i] = i / kKcCand < kKcStage
+                        ? kc_chain_shared(s_xst + (i / kKcCand) * dim, pf + k * dim, dim)
+                        : kc_exact_score<kSlots>(x + (int64_t)(rec & 0xffffu) * dim, pf + k * dim, dim);
         }
       }
       __syncthreads();
@@ -559,7 +613,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
           float bv = -INFINITY;
           int bk = 0;
           for (int k = lane; k < kb; k += 32) {
-            const float v = kc_exact_score<kSlots>(x + (int64_t)r * dim, gpf + k * dim, dim);
+            const float v = kc_exact_score<kSlots>(x + (int64_t)r * dim, pf + k * dim, dim);
             if (v > bv) bv = v, bk = k;
           }
 #pragma unroll

@@ -588,7 +588,8 @@ def test_kmeans_cluster_path_is_taken(monkeypatch):
   monkeypatch.setenv('SPML_B200_KMEANS', 'cluster')
   assert lib.spml_debug_kmeans_path(1, 16384, 66, 36) == 3
   assert lib.spml_debug_kmeans_path(4, 16384, 66, 36) == 3
-  assert lib.spml_debug_kmeans_path(2, 16384, 66, 64) == 3
+  assert lib.spml_debug_kmeans_path(2, 12000, 66, 64) == 3
+  assert lib.spml_debug_kmeans_path(2, 16384, 66, 64) != 3     # (does not fit in shared memory)
   assert lib.spml_debug_kmeans_path(1, 16000, 37, 128) == 3
   assert lib.spml_debug_kmeans_path(1, 3000, 130, 40) == 3
   assert lib.spml_debug_kmeans_path(1, 37636, 66, 128) != 3
