@@ -1,29 +1,33 @@
 // A4-A6 when one image fits in the shared memory of ONE thread-block cluster (K <= 128
-// clusters, every shipped 512 x 512 configuration): spherical k-means with no global-memory
-// traffic and no grid-wide synchronisation between the passes.
+// clusters, the 512 x 512 configurations): spherical k-means with no grid-wide synchronisation
+// and (almost) no global-memory traffic between the passes.
 //
 // kmeans_small.cu spreads an image over ~116 CTAs (one 128-pixel tile each) and separates two
 // passes by an all-to-all through L2: 64-bit reductions into the image's sums, a fence, a tile
-// counter, a poll, and K x dim sums pulled back into every CTA - ~19k cycles per pass at batch
-// 1, of which ~12k are that exchange (profiles/r2_kmeans_small_timeline_b1.txt).  Here
+// counter, a poll, and K x dim sums pulled back into every CTA.  Here
 //   * an image is owned by a cluster of up to 16 CTAs (non-portable size); a CTA keeps its
 //     <= 8 pixel tiles resident as ONE fp16 MMA operand (no-swizzle K-major core matrices, so the
 //     K extent is dim rounded up to 16, not to 64) for all passes: 160 bytes per pixel at
 //     dim = 66;
 //   * the E-step is one fp16 product per score (tcgen05, kind::f16, fp32 accumulation in TMEM,
-//     all tiles of the CTA in flight in separate accumulators).  fp16 inputs bound the error of
-//     a score by 2^-10 |x| (Cauchy-Schwarz), so a row whose best two scores are further apart
-//     than tau = 2^-9 |x| (+ slack) has its exact label; the others (about 1 %) are settled by
-//     the very fmaf chain of the fp32 kernel, evaluated only for the candidates within tau of
-//     the best, one thread per (row, candidate), the fp32 row read from L2;
+//     all tiles of the CTA in flight in separate accumulators, issued by a warp that does
+//     nothing else).  fp16 inputs bound the error of a score by 2^-10 |x| (Cauchy-Schwarz), so
+//     a row whose best two scores are further apart than tau = 2^-9 |x| (+ slack) has its exact
+//     label; the others (about 1 %) are settled by the very fmaf chain of the fp32 kernel,
+//     evaluated only for the candidates within tau of the best, one thread per (row,
+//     candidate), on fp32 rows staged in shared memory with cp.async while the E-step runs;
 //   * the M-step is incremental as in kmeans_small.cu (only rows whose label changed move),
 //     into per-CTA 32-bit shared sums of the two halves of round(x 2^32);
-//   * between two passes: cluster barrier -> CTA r sums the contributions of all CTAs to ITS
-//     prototypes (k = r mod cluster size) through distributed shared memory into running 64-bit
-//     totals, normalises them and stores the fp32 row and the fp16 operand row into every CTA
-//     of the cluster -> cluster barrier.  No L2 round trip on the critical path.
+//   * between two passes: cluster barrier -> CTA r adds, through distributed shared memory and
+//     only from the CTAs whose bit mask says they touched them, the contributions to ITS
+//     prototypes (k = r mod cluster size) to running 64-bit totals, normalises them, stores the
+//     fp16 operand row into every CTA of the cluster (16-byte DSMEM stores) and the fp32 row into
+//     a global scratch (every CTA copies the scratch into its shared memory behind the MMAs)
+//     -> cluster barrier.
 // Sums are exact integers and the recheck is the fp32 chain, so the labels are those of the
 // other three kernels bit for bit (tests/test_gpu_ops.py::test_kmeans_tensor_core_equals_fp32).
+// Measured against kmeans_small.cu in kmeans.cu::kmeans_path (default from batch 4 on) and
+// DESIGN.md section 4; per-phase timeline: scripts/trace_kmeans_cluster.py.
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -100,13 +104,9 @@ __host__ __device__ inline KcLayout kc_layout(int K, int dim, int kp, int bn, in
   return L;
 }
 
-// element (row, d) of a [rows x kp] fp16 K-major operand without swizzle: 8 x 8 core matrices
-// of 128 contiguous bytes; the matrices of one 8-element K chunk follow each other down the
-// rows (UMMA descriptor: SBO = 128, LBO = 16 rows), so that one K step of an MMA streams two
-// contiguous runs of 16 rows bytes instead of 16 pieces a multiple of 32 banks apart
-__device__ __forceinline__ uint32_t kc_operand_offset(int row, int d, int rows) {
-  return (uint32_t)(d >> 3) * (uint32_t)(rows * 16) + (uint32_t)row * 16u + (uint32_t)(d & 7) * 2u;
-}
+// Operand layout (fp16, K-major, no swizzle): 8 x 8 core matrices of 128 contiguous bytes; the
+// matrices of one 8-element K chunk follow each other down the rows, i.e. element (row, d) sits
+// at (d / 8) * rows * 16 + row * 16 + (d % 8) * 2 (UMMA descriptor: SBO = 128, LBO = 16 rows).
 
 // kind::f16 instruction descriptor, fp16 x fp16 -> fp32, both operands K-major
 // (tc_common.cuh::umma_idesc_bf16 with a_format = b_format = 0)
