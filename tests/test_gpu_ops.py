@@ -240,6 +240,28 @@ def test_segment_by_kmeans_edges(units):
       assert torch.equal(a.cpu(), u[k]), k
 
 
+def test_segment_by_kmeans_more_tiles_than_resident_ctas():
+  """12 images of 128 x 128: 3 072 pre-pass tiles (more than can be resident at once: the flat
+  look-back relies on the ticket order) and 12 k-means clusters of 16 CTAs (two waves of the
+  cluster kernel).  Ids bit-exact against the oracle."""
+  g = torch.Generator().manual_seed(41)
+  B, D, H, W = 12, 32, 128, 128
+  centres = torch.randn(50, D, generator=g)
+  region = torch.randint(0, 50, (B, H // 8, W // 8), generator=g)
+  region = region.repeat_interleave(8, 1).repeat_interleave(8, 2)
+  emb = (centres[region] + 0.8 * torch.randn(B, H, W, D, generator=g)).permute(0, 3, 1, 2).contiguous()
+  labels = region.clone()
+  labels[torch.rand(B, H, W, generator=g) < 0.07] = 255
+  labels[5] = 255                                    # an image without pixels
+  want = O.segment_by_kmeans(emb, labels, (6, 6), ignore_index=255, iterations=10)
+  got = segsort_common.segment_by_kmeans(cu(emb), cu(labels), [6, 6], ignore_index=255, iterations=10)
+  for a, b_ in zip(got, want):
+    if a.is_floating_point():
+      close(a.detach(), b_)
+    else:
+      assert torch.equal(a.cpu(), b_)
+
+
 def test_gather_generic_path_equals_fast_path():
   """gather_clustering_and_update_prototypes: the re-numbering path of
   models/utils.py:95-108 and the shortcut for ids fresh from segment_by_kmeans."""
