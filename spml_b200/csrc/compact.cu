@@ -144,6 +144,57 @@ __global__ void unique_inverse_kernel(const int32_t* __restrict__ slot_of,
   if (i < live_keys(n, n_dev)) inverse[i] = rank_of_slot[slot_of[i]];
 }
 
+// ---- the three phases of spml_unique_inverse, separately, for a caller that overlaps them with
+// other work (pipeline.cu: the preparation runs beside the k-means, the count of distinct keys
+// is final after the insertion and goes to the host while the ranking still runs)
+
+// count = 0, empty table, running maximum of lo (when the bound is to be derived from it)
+int unique_prepare(bool has_hi, const int64_t* lo, int64_t n, const int32_t* n_dev, int64_t bound,
+                   int32_t* count, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  SPML_CHECK_ARG(n >= 0 && count && bound >= 0, "unique_inverse: bad arguments");
+  SPML_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+  if (n == 0) return SPML_OK;
+  SPML_CHECK_ARG(lo && workspace, "unique_inverse: null pointer");
+  SPML_CHECK_SUPPORTED(n < (1ll << 30), "unique_inverse: more than 2^30 keys");
+  UniqueWs w = carve(workspace, n);
+  if (workspace_bytes < w.bytes) {
+    set_error("unique_inverse: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    return SPML_E_WORKSPACE;
+  }
+  // max_lo and the table share the 0x80 fill: "very negative" / "empty"
+  SPML_CUDA(cudaMemsetAsync(workspace, 0x80, 16 + (size_t)w.cap * 8, st));
+  if (bound == 0 && has_hi) {
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    max_lo_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(lo, n, n_dev, w.max_lo);
+    SPML_LAUNCH_CHECK("max_lo_kernel");
+  }
+  return SPML_OK;
+}
+
+// distinct keys into the table; *count is final when this kernel is
+int unique_insert(const int64_t* hi, const int64_t* lo, int64_t n, const int32_t* n_dev,
+                  int64_t bound, int32_t* count, void* workspace, cudaStream_t st) {
+  UniqueWs w = carve(workspace, n);
+  unique_insert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+      hi, lo, n, n_dev, bound, w.max_lo, w.table, w.cap - 1, w.slot_of, w.distinct, count);
+  SPML_LAUNCH_CHECK("unique_insert_kernel");
+  return SPML_OK;
+}
+
+// rank of the distinct keys, inverse map
+int unique_finish(bool has_hi, int64_t n, const int32_t* n_dev, int64_t bound, int64_t* inverse,
+                  int64_t* uniq_hi, int64_t* uniq_lo, const int32_t* count, int64_t* bound_out,
+                  void* workspace, cudaStream_t st) {
+  UniqueWs w = carve(workspace, n);
+  const unsigned blocks = (unsigned)ceil_div(n, 256);
+  unique_rank_kernel<<<blocks, 256, 0, st>>>(w.table, w.distinct, count, has_hi, bound, w.max_lo,
+                                             w.rank_of_slot, uniq_hi, uniq_lo, bound_out);
+  SPML_LAUNCH_CHECK("unique_rank_kernel");
+  unique_inverse_kernel<<<blocks, 256, 0, st>>>(w.slot_of, w.rank_of_slot, n, n_dev, inverse);
+  SPML_LAUNCH_CHECK("unique_inverse_kernel");
+  return SPML_OK;
+}
+
 }  // namespace spml
 
 extern "C" {
@@ -158,34 +209,13 @@ int spml_unique_inverse(const int64_t* hi, const int64_t* lo, int64_t n, const i
                         int64_t* bound_out, void* workspace, size_t workspace_bytes,
                         void* stream) {
   using namespace spml;
-  SPML_CHECK_ARG(n >= 0 && count && bound >= 0, "unique_inverse: bad arguments");
   cudaStream_t st = as_stream(stream);
-  SPML_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
-  if (n == 0) return SPML_OK;
-  SPML_CHECK_ARG(lo && inverse && workspace, "unique_inverse: null pointer");
-  SPML_CHECK_SUPPORTED(n < (1ll << 30), "unique_inverse: more than 2^30 keys");
-  UniqueWs w = carve(workspace, n);
-  if (workspace_bytes < w.bytes) {
-    set_error("unique_inverse: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
-    return SPML_E_WORKSPACE;
-  }
-  // max_lo and the table share the 0x80 fill: "very negative" / "empty"
-  SPML_CUDA(cudaMemsetAsync(workspace, 0x80, 16 + (size_t)w.cap * 8, st));
-  const unsigned blocks = (unsigned)ceil_div(n, 256);
-  if (bound == 0 && hi) {
-    max_lo_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(lo, n, n_dev, w.max_lo);
-    SPML_LAUNCH_CHECK("max_lo_kernel");
-  }
-  unique_insert_kernel<<<blocks, 256, 0, st>>>(hi, lo, n, n_dev, bound, w.max_lo, w.table, w.cap - 1,
-                                               w.slot_of, w.distinct, count);
-  SPML_LAUNCH_CHECK("unique_insert_kernel");
-  unique_rank_kernel<<<blocks, 256, 0, st>>>(w.table, w.distinct, count, hi != nullptr, bound,
-                                             w.max_lo, w.rank_of_slot, uniq_hi, uniq_lo,
-                                             bound_out);
-  SPML_LAUNCH_CHECK("unique_rank_kernel");
-  unique_inverse_kernel<<<blocks, 256, 0, st>>>(w.slot_of, w.rank_of_slot, n, n_dev, inverse);
-  SPML_LAUNCH_CHECK("unique_inverse_kernel");
-  return SPML_OK;
+  int rc = unique_prepare(hi != nullptr, lo, n, n_dev, bound, count, workspace, workspace_bytes, st);
+  if (rc != SPML_OK || n == 0) return rc;
+  SPML_CHECK_ARG(inverse, "unique_inverse: null pointer");
+  if ((rc = unique_insert(hi, lo, n, n_dev, bound, count, workspace, st)) != SPML_OK) return rc;
+  return unique_finish(hi != nullptr, n, n_dev, bound, inverse, uniq_hi, uniq_lo, count, bound_out,
+                       workspace, st);
 }
 
 }  // extern "C"

@@ -37,6 +37,16 @@ int segsort_bwd_impl(const spml_segsort_desc* d, const float* stats, const float
 int segsort_reduce_two(const float* pa, int ca, const float* pb, int cb, int64_t count, float* out,
                        cudaStream_t st);
 
+// compact.cu: the phases of spml_unique_inverse (preparation / insertion, after which *count is
+// final / ranking + inverse map)
+int unique_prepare(bool has_hi, const int64_t* lo, int64_t n, const int32_t* n_dev, int64_t bound,
+                   int32_t* count, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int unique_insert(const int64_t* hi, const int64_t* lo, int64_t n, const int32_t* n_dev,
+                  int64_t bound, int32_t* count, void* workspace, cudaStream_t st);
+int unique_finish(bool has_hi, int64_t n, const int32_t* n_dev, int64_t bound, int64_t* inverse,
+                  int64_t* uniq_hi, int64_t* uniq_lo, const int32_t* count, int64_t* bound_out,
+                  void* workspace, cudaStream_t st);
+
 // normalize.cu: label packing + valid-pixel scan + normalise / pack in one launch (A8 front half)
 int scan_normalize_pack(const float* emb, const float* loc, int64_t loc_batch_stride, int loc_ch,
                         const int64_t* labels, int has_ignore, int64_t ignore_index,

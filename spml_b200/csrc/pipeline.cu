@@ -27,6 +27,7 @@ struct StreamPool {
   cudaStream_t side[kSideStreams];
   cudaEvent_t fork;
   cudaEvent_t join[kSideStreams];
+  cudaEvent_t counts;   // the count read-back of the clustering stage has landed
 };
 
 // One pool per (host thread, device): the reference drives every GPU from its own Python
@@ -47,6 +48,7 @@ static int get_pool(StreamPool** out) {
       SPML_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
     }
     SPML_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    SPML_CUDA(cudaEventCreateWithFlags(&p.counts, cudaEventDisableTiming));
     p.ready = true;
   }
   *out = &p;
@@ -592,24 +594,36 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
                                      a->batch_index_offset, a->eps, a->e, a->el, a->nx, a->nc,
                                      a->labels_out, a->batch_out, a->seed_out, stream));
   }
+  // The table of the id numbering is cleared, and the largest label found, beside the k-means
+  // (side stream); the number of segments is final once the distinct (image, cluster, label)
+  // keys are in the table, so it goes to the host right then and the ranking of the keys runs
+  // while the host already prepares the next stage.
+  const int32_t* rows_dev = a->img_off + a->batch;
+  StreamPool* pool = nullptr;
+  SPML_TRY(get_pool(&pool));
+  SPML_TRY(fork_streams(*pool, st, 1));
+  SPML_TRY(unique_prepare(true, a->labels_out, cap, rows_dev, 0, a->num_segments, uq_ws, uq_bytes,
+                          pool->side[0]));
   SPML_TRY(spml_kmeans(a->el, a->img_off, a->batch, a->n, dl, a->num_clusters, a->k_per_image,
                        a->iterations, a->seed_out, a->kmeans_labels, nullptr, km_ws, km_bytes,
                        stream));
-  const int32_t* rows_dev = a->img_off + a->batch;
   cluster_key_kernel<<<blocks_of(cap), 256, 0, st>>>(a->kmeans_labels, a->batch_out, cap, rows_dev,
                                                     a->num_clusters, key_hi, a->labels_out,
                                                     a->label_divisor, a->sem_out, a->inst_out);
   SPML_LAUNCH_CHECK("cluster_key_kernel");
-  SPML_TRY(spml_unique_inverse(key_hi, a->labels_out, cap, rows_dev, 0, a->segment_ids, nullptr,
-                               nullptr, a->num_segments, nullptr, uq_ws, uq_bytes, stream));
+  SPML_TRY(join_stream(*pool, 0, st));
+  SPML_TRY(unique_insert(key_hi, a->labels_out, cap, rows_dev, 0, a->num_segments, uq_ws, st));
   if (a->counts_host) {
     SPML_CHECK_ARG(a->counts_dev, "segment_by_kmeans: counts_host needs counts_dev");
     publish_counts_kernel<<<1, 32, 0, st>>>(rows_dev, a->num_segments, a->status, a->counts_dev);
     SPML_LAUNCH_CHECK("publish_counts_kernel");
     SPML_CUDA(cudaMemcpyAsync(a->counts_host, a->counts_dev, 4 * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, st));
-    SPML_CUDA(cudaStreamSynchronize(st));
+    SPML_CUDA(cudaEventRecord(pool->counts, st));
   }
+  SPML_TRY(unique_finish(true, cap, rows_dev, 0, a->segment_ids, nullptr, nullptr, a->num_segments,
+                         nullptr, uq_ws, st));
+  if (a->counts_host) SPML_CUDA(cudaEventSynchronize(pool->counts));
   return SPML_OK;
 }
 
