@@ -100,6 +100,65 @@ __global__ void unique_insert_kernel(const int64_t* __restrict__ hi, const int64
   slot_of[i] = (int32_t)h;
 }
 
+// unique_insert_kernel for the tail of the clustering stage (pipeline.cu), with what used to be
+// two more launches on the way to the step's host read-back folded in:
+//  * the key is built on the fly: high part (image, k-means cluster), low part the pixel's label
+//    (common.py:398-405), and the label is decoded into its semantic / instance parts
+//    (resnet_deeplab.py:134-135: floor division / modulo);
+//  * the LAST block to finish publishes {rows kept, segments, status, 0} - the number of distinct
+//    keys is final then - into device memory and, with a sequence number behind a system-scope
+//    fence, into pinned host memory that the host polls.  The ticket counter is the spare half of
+//    the workspace header (filled with 0x80 by the same memset as the table).
+__global__ void cluster_insert_kernel(const int32_t* __restrict__ km, const int64_t* __restrict__ batch,
+                                      const int64_t* __restrict__ lo, int64_t n,
+                                      const int32_t* __restrict__ n_dev, int64_t num_clusters,
+                                      const long long* max_lo, unsigned long long* table,
+                                      int64_t cap_mask, int32_t* __restrict__ slot_of,
+                                      int32_t* distinct, int32_t* count, int64_t divisor,
+                                      int64_t* __restrict__ sem_out, int64_t* __restrict__ inst_out,
+                                      unsigned* ticket, int32_t* status, int32_t* counts_out,
+                                      int32_t* host_out, int32_t seq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < live_keys(n, n_dev)) {
+    const long long lab = lo[i];
+    const long long key = lab + ((long long)km[i] + batch[i] * num_clusters) * (*max_lo + 1);
+    const unsigned long long ukey = (unsigned long long)key;
+    int64_t h = (int64_t)(mix64(ukey) & (unsigned long long)cap_mask);
+    while (true) {
+      const unsigned long long prev = atomicCAS(&table[h], kEmptyKey, ukey);
+      if (prev == kEmptyKey) {
+        distinct[atomicAdd(count, 1)] = (int32_t)h;
+        break;
+      }
+      if (prev == ukey) break;
+      h = (h + 1) & cap_mask;
+    }
+    slot_of[i] = (int32_t)h;
+    if (sem_out) {
+      int64_t q = lab / divisor, m = lab % divisor;
+      if (m != 0 && ((m < 0) != (divisor < 0))) --q, m += divisor;
+      sem_out[i] = q;
+      inst_out[i] = m;
+    }
+  }
+  if (!counts_out) return;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(ticket, 1u) != 0x80808080u + gridDim.x - 1u) return;
+  __threadfence();
+  const int32_t r = *reinterpret_cast<const volatile int32_t*>(n_dev);
+  const int32_t m = *reinterpret_cast<volatile int32_t*>(count);
+  const int32_t st = status ? atomicExch(status, 0) : 0;
+  counts_out[0] = r, counts_out[1] = m, counts_out[2] = st, counts_out[3] = 0;
+  if (host_out) {
+    volatile int32_t* hp = host_out;
+    hp[0] = r, hp[1] = m, hp[2] = st, hp[3] = 0;
+    __threadfence_system();
+    hp[4] = seq;
+  }
+}
+
 // rank of every distinct key = number of distinct keys that are smaller (signed order)
 __global__ void unique_rank_kernel(const unsigned long long* __restrict__ table,
                                    const int32_t* __restrict__ distinct,
@@ -178,6 +237,19 @@ int unique_insert(const int64_t* hi, const int64_t* lo, int64_t n, const int32_t
   unique_insert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
       hi, lo, n, n_dev, bound, w.max_lo, w.table, w.cap - 1, w.slot_of, w.distinct, count);
   SPML_LAUNCH_CHECK("unique_insert_kernel");
+  return SPML_OK;
+}
+
+int cluster_insert(const int32_t* km, const int64_t* batch, const int64_t* labels, int64_t n,
+                   const int32_t* n_dev, int64_t num_clusters, int32_t* count, int64_t divisor,
+                   int64_t* sem_out, int64_t* inst_out, int32_t* status, int32_t* counts_out,
+                   int32_t* host_out, int32_t seq, void* workspace, cudaStream_t st) {
+  UniqueWs w = carve(workspace, n);
+  cluster_insert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+      km, batch, labels, n, n_dev, num_clusters, w.max_lo, w.table, w.cap - 1, w.slot_of, w.distinct,
+      count, divisor, sem_out, inst_out, reinterpret_cast<unsigned*>(w.max_lo + 1), status,
+      counts_out, host_out, seq);
+  SPML_LAUNCH_CHECK("cluster_insert_kernel");
   return SPML_OK;
 }
 

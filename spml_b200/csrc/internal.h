@@ -43,6 +43,12 @@ int unique_prepare(bool has_hi, const int64_t* lo, int64_t n, const int32_t* n_d
                    int32_t* count, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int unique_insert(const int64_t* hi, const int64_t* lo, int64_t n, const int32_t* n_dev,
                   int64_t bound, int32_t* count, void* workspace, cudaStream_t st);
+// (the insertion for the keys (image, k-means cluster, label) of the clustering stage, built on
+// the fly; its last block publishes {rows, segments, status} to device and pinned host memory)
+int cluster_insert(const int32_t* km, const int64_t* batch, const int64_t* labels, int64_t n,
+                   const int32_t* n_dev, int64_t num_clusters, int32_t* count, int64_t divisor,
+                   int64_t* sem_out, int64_t* inst_out, int32_t* status, int32_t* counts_out,
+                   int32_t* host_out, int32_t seq, void* workspace, cudaStream_t st);
 int unique_finish(bool has_hi, int64_t n, const int32_t* n_dev, int64_t bound, int64_t* inverse,
                   int64_t* uniq_hi, int64_t* uniq_lo, const int32_t* count, int64_t* bound_out,
                   void* workspace, cudaStream_t st);

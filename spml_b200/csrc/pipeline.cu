@@ -10,6 +10,7 @@
 // accuracy) run on a small per-thread pool of side streams that fork from and join back into
 // the caller's stream, so the call is still "everything enqueued on `stream`" for the caller.
 #include <algorithm>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,7 +28,13 @@ struct StreamPool {
   cudaStream_t side[kSideStreams];
   cudaEvent_t fork;
   cudaEvent_t join[kSideStreams];
-  cudaEvent_t counts;   // the count read-back of the clustering stage has landed
+  // count read-back of the clustering stage: the kernel stores {rows, segments, status, 0, seq}
+  // straight into pinned host memory and the host polls `seq` (a 16-byte cudaMemcpyAsync into
+  // pageable memory + synchronise costs ~10 us of copy-engine and driver latency on the one
+  // host-device round trip of the step)
+  int32_t* host_counts;       // pinned, mapped: 8 words
+  int32_t* host_counts_dev;   // the same words as the device sees them
+  int32_t seq;
 };
 
 // One pool per (host thread, device): the reference drives every GPU from its own Python
@@ -48,7 +55,11 @@ static int get_pool(StreamPool** out) {
       SPML_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
     }
     SPML_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
-    SPML_CUDA(cudaEventCreateWithFlags(&p.counts, cudaEventDisableTiming));
+    SPML_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p.host_counts), 8 * sizeof(int32_t),
+                            cudaHostAllocMapped));
+    for (int i = 0; i < 8; ++i) p.host_counts[i] = 0;
+    SPML_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.host_counts_dev), p.host_counts, 0));
+    p.seq = 0;
     p.ready = true;
   }
   *out = &p;
@@ -92,36 +103,6 @@ struct Carver {
 };
 
 // ------------------------------------------------------------------------- A8 kernels
-
-// key of a pixel for the final ids: (image, k-means cluster) as the high part; the low
-// part is the pixel's label (common.py:398-405).
-__global__ void cluster_key_kernel(const int32_t* __restrict__ km, const int64_t* __restrict__ batch,
-                                   int64_t cap, const int32_t* __restrict__ rows_dev,
-                                   int64_t num_clusters, int64_t* __restrict__ hi,
-                                   const int64_t* __restrict__ labels, int64_t divisor,
-                                   int64_t* __restrict__ sem_out, int64_t* __restrict__ inst_out) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= cap || r >= (int64_t)*rows_dev) return;
-  hi[r] = (int64_t)km[r] + batch[r] * num_clusters;
-  if (sem_out) {          // resnet_deeplab.py:134-135: floor division / modulo of the label
-    const int64_t lab = labels[r];
-    int64_t q = lab / divisor, m = lab % divisor;
-    if (m != 0 && ((m < 0) != (divisor < 0))) --q, m += divisor;
-    sem_out[r] = q;
-    inst_out[r] = m;
-  }
-}
-
-// {rows kept, segments, status} next to each other for ONE device->host copy; the status word
-// is handed over (reset) here
-__global__ void publish_counts_kernel(const int32_t* rows, const int32_t* segments, int32_t* status,
-                                      int32_t* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  out[0] = *rows;
-  out[1] = *segments;
-  out[2] = status ? atomicExch(status, 0) : 0;
-  out[3] = 0;
-}
 
 constexpr int64_t kDroppedLabel = 0x7fffffffffffffffll;
 
@@ -556,7 +537,7 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
   const int64_t cap = (int64_t)a->batch * a->n;
   const size_t uq_bytes = spml_unique_workspace_bytes(cap);
   void* uq_ws = c.take_bytes(uq_bytes);
-  int64_t* key_hi = c.take<int64_t>((size_t)cap);
+  (void)c.take<int64_t>((size_t)cap);   // (room of the former key array: the keys are built on the fly)
   int64_t* packed = c.take<int64_t>((size_t)cap);
   cudaStream_t st = as_stream(stream);
 
@@ -607,23 +588,36 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
   SPML_TRY(spml_kmeans(a->el, a->img_off, a->batch, a->n, dl, a->num_clusters, a->k_per_image,
                        a->iterations, a->seed_out, a->kmeans_labels, nullptr, km_ws, km_bytes,
                        stream));
-  cluster_key_kernel<<<blocks_of(cap), 256, 0, st>>>(a->kmeans_labels, a->batch_out, cap, rows_dev,
-                                                    a->num_clusters, key_hi, a->labels_out,
-                                                    a->label_divisor, a->sem_out, a->inst_out);
-  SPML_LAUNCH_CHECK("cluster_key_kernel");
   SPML_TRY(join_stream(*pool, 0, st));
-  SPML_TRY(unique_insert(key_hi, a->labels_out, cap, rows_dev, 0, a->num_segments, uq_ws, st));
   if (a->counts_host) {
     SPML_CHECK_ARG(a->counts_dev, "segment_by_kmeans: counts_host needs counts_dev");
-    publish_counts_kernel<<<1, 32, 0, st>>>(rows_dev, a->num_segments, a->status, a->counts_dev);
-    SPML_LAUNCH_CHECK("publish_counts_kernel");
-    SPML_CUDA(cudaMemcpyAsync(a->counts_host, a->counts_dev, 4 * sizeof(int32_t),
-                              cudaMemcpyDeviceToHost, st));
-    SPML_CUDA(cudaEventRecord(pool->counts, st));
+    pool->seq = pool->seq == 0x7fffffff ? 1 : pool->seq + 1;
   }
+  // keys (image, cluster, label) into the table, labels decoded, counts published by the last block
+  SPML_TRY(cluster_insert(a->kmeans_labels, a->batch_out, a->labels_out, cap, rows_dev,
+                          a->num_clusters, a->num_segments, a->label_divisor, a->sem_out, a->inst_out,
+                          a->status, a->counts_host ? a->counts_dev : nullptr,
+                          a->counts_host ? pool->host_counts_dev : nullptr, pool->seq, uq_ws, st));
   SPML_TRY(unique_finish(true, cap, rows_dev, 0, a->segment_ids, nullptr, nullptr, a->num_segments,
                          nullptr, uq_ws, st));
-  if (a->counts_host) SPML_CUDA(cudaEventSynchronize(pool->counts));
+  if (a->counts_host) {
+    // the step's one wait for the device: poll the sequence number; look at the stream now and
+    // then so that a failed kernel surfaces as an error instead of a hang
+    volatile int32_t* h = pool->host_counts;
+    for (unsigned spins = 1; h[4] != pool->seq; ++spins) {
+      if ((spins & 0x3ffu) == 0) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) {
+          if (h[4] == pool->seq) break;
+          set_error("segment_by_kmeans: the stream drained without publishing the counts");
+          return SPML_E_CUDA;
+        }
+        if (q != cudaErrorNotReady) return cuda_fail(q, "segment_by_kmeans: waiting for the counts");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int i = 0; i < 4; ++i) a->counts_host[i] = h[i];
+  }
   return SPML_OK;
 }
 
