@@ -37,6 +37,12 @@ int segsort_bwd_impl(const spml_segsort_desc* d, const float* stats, const float
 int segsort_reduce_two(const float* pa, int ca, const float* pb, int cb, int64_t count, float* out,
                        cudaStream_t st);
 
+// topk_tc.cu: top_k_ranking on the tensor cores for a large prototype bank (no masks / groups)
+bool topk_tc_supported(int64_t nq, int64_t m, int dim, int k);
+int topk_tc_launch(const float* q, int64_t nq, const float* p, int64_t m, int dim,
+                   const int64_t* qlab, const int64_t* plab, int k, int64_t* topk_labels,
+                   int64_t* topk_index, int32_t* hit_count, cudaStream_t st);
+
 // compact.cu: the phases of spml_unique_inverse (preparation / insertion, after which *count is
 // final / ranking + inverse map)
 int unique_prepare(bool has_hi, const int64_t* lo, int64_t n, const int32_t* n_dev, int64_t bound,

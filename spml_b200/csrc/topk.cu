@@ -291,6 +291,12 @@ int topk_launch(const float* q, int64_t nq, const float* p, int64_t m, int dim,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const bool extra_on = extra.qgroup || extra.pgroup || extra.has_limit || extra.sim;
+  // a large bank without masks (retrieval inference): tcgen05 candidates + exact re-scoring
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  SPML_CUDA(cudaStreamIsCapturing(st, &capturing));   // (its scratch may have to be allocated)
+  if (!extra_on && !qvalid && !pvalid && capturing == cudaStreamCaptureStatusNone &&
+      topk_tc_supported(nq, m, dim, k))
+    return topk_tc_launch(q, nq, p, m, dim, qlab, plab, k, topk_labels, topk_index, hit_count, st);
 #define SPML_TOPK_LAUNCH(KMAXV, QWV, EXTRAV)                                                    \
   do {                                                                                          \
     SPML_CUDA(cudaFuncSetAttribute(topk_kernel<KMAXV, QWV, EXTRAV>,                             \

@@ -570,6 +570,43 @@ def test_retrieval_at_inference_scale():
   assert float((pred.cpu() != want_pred).float().mean()) < 1e-3
 
 
+@pytest.mark.parametrize('nq,m,dim,k', [(576, 50000, 64, 20), (130, 9000, 37, 5), (1000, 4097, 128, 20),
+                                        (7, 5000, 64, 3), (300, 6000, 66, 24)])
+def test_topk_tensor_core_equals_fma(nq, m, dim, k, monkeypatch):
+  """topk_tc.cu (tcgen05 candidates + exact re-scoring) returns the indices of the FMA kernel:
+  ragged tiles, K padding, two K blocks, duplicated bank rows (ties resolve to the lower index)."""
+  from spml_b200 import _lib
+  g = torch.Generator().manual_seed(nq + m)
+  centres = O.l2_normalize(torch.randn(64, dim, generator=g))
+  q = O.l2_normalize(centres[torch.randint(0, 64, (nq,), generator=g)] + 0.3 * torch.randn(nq, dim, generator=g))
+  p = O.l2_normalize(centres[torch.randint(0, 64, (m,), generator=g)] + 0.3 * torch.randn(m, dim, generator=g))
+  p[m // 2:m // 2 + 40] = p[3]                       # 41 identical rows
+  p[m - 17:] = p[5]
+  qlab = torch.randint(0, 21, (nq,), generator=g)
+  plab = torch.randint(0, 21, (m,), generator=g)
+  got = {}
+  for path in ('fma', 'tc'):
+    monkeypatch.setenv('SPML_B200_TOPK', path)
+    labels = torch.zeros(nq, k, dtype=torch.int64, device='cuda')
+    index = torch.zeros(nq, k, dtype=torch.int64, device='cuda')
+    hits = torch.empty(2, dtype=torch.int32, device='cuda')
+    qc, pc, qlc, plc = cu(q), cu(p), cu(qlab), cu(plab)   # (kept alive: the call takes raw pointers)
+    ops.call('spml_topk_ranking', ops.ptr(qc), nq, ops.ptr(pc), m, dim, ops.ptr(qlc),
+             ops.ptr(plc), None, None, k, ops.ptr(labels), ops.ptr(index), ops.ptr(hits),
+             ops.stream_of(qc))
+    torch.cuda.synchronize()
+    got[path] = (labels.cpu(), index.cpu(), hits.cpu())
+  assert torch.equal(got['fma'][1], got['tc'][1]), int((got['fma'][1] != got['tc'][1]).sum())
+  assert torch.equal(got['fma'][0], got['tc'][0])
+  want_hits = int((got['tc'][0] == qlab.view(-1, 1)).sum())
+  assert [int(v) for v in got['tc'][2]] == [want_hits, nq], (got['tc'][2], want_hits)
+  assert [int(v) for v in got['fma'][2]] == [want_hits, nq], (got['fma'][2], want_hits)
+  # ... and the order of the reference's argsort where the scores are well separated
+  sim = q.double() @ p.double().t()
+  want = torch.argsort(sim, dim=1, descending=True, stable=True)[:, :k]
+  assert float((want != got['tc'][1]).float().mean()) < 2e-3      # near-ties in fp32 may swap
+
+
 def test_random_walk_matches_oracle():
   """SURVEY.md 8f-4 (pseudo_softmaxrw_crf.py:135-170)."""
   from spml_b200 import random_walk
