@@ -262,6 +262,27 @@ def test_segment_by_kmeans_more_tiles_than_resident_ctas():
       assert torch.equal(a.cpu(), b_)
 
 
+@pytest.mark.parametrize('path', ['cluster', 'small', 'fp32'])
+def test_segment_by_kmeans_clusters_per_image_differ(path, monkeypatch):
+  """User-supplied seed maps with a different number of clusters in every image (k_per_image):
+  4 images, so the default would be the cluster kernel; every kernel against the oracle."""
+  monkeypatch.setenv('SPML_B200_KMEANS', path)
+  g = torch.Generator().manual_seed(13)
+  B, D, H, W = 4, 16, 48, 40
+  emb = torch.randn(B, D, H, W, generator=g)
+  labels = torch.randint(0, 5, (B, H, W), generator=g)
+  ks = (5, 9, 1, 7)
+  cmap = torch.stack([(torch.arange(H * W) * k // (H * W)).view(H, W) * 3 + 2 for k in ks])   # ids with gaps
+  want = O.segment_by_kmeans(emb, labels, (3, 3), cluster_indices=cmap, iterations=6)
+  got = segsort_common.segment_by_kmeans(cu(emb), cu(labels), [3, 3], cluster_indices=cu(cmap),
+                                         iterations=6)
+  for a, b_ in zip(got, want):
+    if a.is_floating_point():
+      close(a.detach(), b_)
+    else:
+      assert torch.equal(a.cpu(), b_)
+
+
 def test_gather_generic_path_equals_fast_path():
   """gather_clustering_and_update_prototypes: the re-numbering path of
   models/utils.py:95-108 and the shortcut for ids fresh from segment_by_kmeans."""
