@@ -33,7 +33,7 @@ namespace spml {
 
 constexpr int kTtRows = 128;                 // queries per CTA (UMMA M)
 constexpr int kTtCols = 128;                 // bank rows per tile (UMMA N; N = 256 with the lo part)
-constexpr int kTtThreads = 256;
+constexpr int kTtThreads = 512;             // 16 warps: the row phase is a latency-bound shuffle chain per row
 constexpr int kTtMaxC = 32;                  // candidates per list: k + 8 <= 32
 constexpr int kTtBlockBytes = 128 * 128;     // one 64-wide K block of a 128-row bf16 tile
 constexpr int kTtLd = kTtCols + 1;           // row stride of the score tile in shared memory
@@ -97,6 +97,70 @@ __device__ __forceinline__ void tt_split_tile(const float* __restrict__ x, int64
   }
 }
 
+// (score, index) order of the lists: higher score first, lower index first on equal scores
+__device__ __forceinline__ bool tt_better(float va, int ia, float vb, int ib) {
+  return (va > vb) | ((va == vb) & (ia < ib));   // (bitwise: no short-circuit branches)
+}
+// N independent sequences of one element per lane -> each sorted best-first across the warp
+// (bitonic network, 15 exchanges; the N chains are interleaved step by step, because a single
+// chain is nothing but shuffle latency: 4 sorts one after the other took ~12k cycles per row)
+template <int N>
+__device__ __forceinline__ void tt_sort32(float (&v)[N], int (&i)[N], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool want_better = ((lane & j) == 0) == ((lane & k) == 0);
+      float ov[N];
+      int oi[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        ov[n] = __shfl_xor_sync(0xffffffffu, v[n], j);
+        oi[n] = __shfl_xor_sync(0xffffffffu, i[n], j);
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        // (keys are distinct: "the other one is better" decides both directions; selects, no branches)
+        const bool other_better = tt_better(ov[n], oi[n], v[n], i[n]);
+        const bool take = other_better == want_better;
+        v[n] = take ? ov[n] : v[n];
+        i[n] = take ? oi[n] : i[n];
+      }
+    }
+  }
+}
+// N pairs of sequences sorted best-first across the warp -> the best 32 of each pair's 64,
+// sorted, in (v[n], i[n]); interleaved like tt_sort32
+template <int N>
+__device__ __forceinline__ void tt_merge32(float (&v)[N], int (&i)[N], const float (&bv)[N],
+                                           const int (&bi)[N], int lane) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float rv = __shfl_sync(0xffffffffu, bv[n], 31 - lane);
+    const int ri = __shfl_sync(0xffffffffu, bi[n], 31 - lane);
+    const bool take = tt_better(rv, ri, v[n], i[n]);                  // bitonic, holds the best 32
+    v[n] = take ? rv : v[n];
+    i[n] = take ? ri : i[n];
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    float ov[N];
+    int oi[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      ov[n] = __shfl_xor_sync(0xffffffffu, v[n], j);
+      oi[n] = __shfl_xor_sync(0xffffffffu, i[n], j);
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const bool other_better = tt_better(ov[n], oi[n], v[n], i[n]);
+      const bool take = other_better == ((lane & j) == 0);
+      v[n] = take ? ov[n] : v[n];
+      i[n] = take ? oi[n] : i[n];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const TopkTcArgs a) {
   extern __shared__ uint8_t tt_smem_raw[];
   __shared__ __align__(8) uint64_t bar_done;
@@ -138,17 +202,26 @@ __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const
   const uint32_t al_lo = tc::umma_desc_lo(tc::smem_u32(a_lo), 16);
   const uint32_t b_lo = tc::umma_desc_lo(tc::smem_u32(b_tile), 16);
 
-  const int sp = warp & 3, half = warp >> 2;
+  const int sp = warp & 3, quarter = warp >> 2;   // TMEM sub-partition, 32-column quarter of the tile
   const int row = sp * 32 + lane;
   const int64_t ntiles = (a.m + kTtCols - 1) / kTtCols;
   uint32_t phase = 0;
 
+#ifdef SPML_TT_TRACE
+  long long tt_t[6] = {0, 0, 0, 0, 0, 0}, tt_c = clock64();
+  int tt_events = 0, tt_visits = 0;
+#define TT_MARK(i) do { const long long n__ = clock64(); tt_t[i] += n__ - tt_c; tt_c = n__; } while (0)
+#else
+#define TT_MARK(i) do { } while (0)
+#endif
   for (int64_t t = slice; t < ntiles; t += a.slices) {
     const int64_t c0 = t * kTtCols;
+    TT_MARK(0);
     // ---- bank tile -> bf16 hi | lo operand (hi part then lo part inside every K block)
     tt_split_tile(a.p, c0, a.m, a.dim, a.nkb, b_tile, kTtBlockBytes, 2 * kTtBlockBytes);
     tc::fence_proxy_async();
     __syncthreads();
+    TT_MARK(1);
     if (warp == 0) {
       tc::tcgen05_fence_after();
       if (tc::elect_one()) {
@@ -171,10 +244,10 @@ __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const
     tc::mbar_wait(&bar_done, phase);
     phase ^= 1u;
     tc::tcgen05_fence_after();
-    // ---- TMEM -> shared memory: this thread's row, its 64 columns; columns past the bank = -inf
-#pragma unroll
-    for (int chunk = 0; chunk < 2; ++chunk) {
-      const int cb = half * 64 + chunk * 32;
+    TT_MARK(2);
+    // ---- TMEM -> shared memory: this thread's row, its 32 columns; columns past the bank = -inf
+    {
+      const int cb = quarter * 32;
       uint32_t v[32], w[32];
       const uint32_t taddr = tmem_base + cb + (static_cast<uint32_t>(sp * 32) << 16);
       tc::tmem_ld_32x32(taddr, v);              // hi.hi + lo.hi
@@ -187,9 +260,39 @@ __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const
     }
     tc::tcgen05_fence_before();
     __syncthreads();
+    TT_MARK(3);
     // ---- the warps take the rows one at a time
-    for (int r = warp * (kTtRows / 8); r < (warp + 1) * (kTtRows / 8); ++r) {
+    constexpr int kRowsPerWarp = kTtRows / (kTtThreads / 32);
+    for (int r = warp * kRowsPerWarp; r < (warp + 1) * kRowsPerWarp; ++r) {
       if (q0 + r >= a.nq) break;   // warp-uniform
+      if (t == slice) {
+        // the first tile of this CTA: the list is empty and every score would be inserted one
+        // at a time (128 dependent insertions per row: ~100 us per CTA); sort the four blocks
+        // of 32 scores and merge them instead
+        float sv[4];
+        int si[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sv[j] = s_sc[r * kTtLd + 32 * j + lane];
+          si[j] = sv[j] == -INFINITY ? 0x7fffffff : (int)(c0 + 32 * j + lane);
+        }
+        tt_sort32<4>(sv, si, lane);
+        {
+          float av[2] = {sv[0], sv[2]}, bv[2] = {sv[1], sv[3]};
+          int ai[2] = {si[0], si[2]}, bi[2] = {si[1], si[3]};
+          tt_merge32<2>(av, ai, bv, bi, lane);          // blocks 0 + 1 and 2 + 3
+          float cv[1] = {av[0]}, dv[1] = {av[1]};
+          int ci[1] = {ai[0]}, di[1] = {ai[1]};
+          tt_merge32<1>(cv, ci, dv, di, lane);
+          sv[0] = cv[0], si[0] = ci[0];
+        }
+        if (lane >= C) sv[0] = -INFINITY, si[0] = 0x7fffffff;
+        l_val[r * 32 + lane] = sv[0];
+        l_idx[r * 32 + lane] = si[0];
+        const float t0 = __shfl_sync(0xffffffffu, sv[0], C - 1);
+        if (lane == 0) s_thr[r] = t0;
+        continue;
+      }
       float thr = s_thr[r];
       float xs[4];
       unsigned pass[4];
@@ -201,6 +304,9 @@ __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const
         any |= pass[j];
       }
       if (!any) continue;
+#ifdef SPML_TT_TRACE
+      ++tt_visits;
+#endif
       float lv = l_val[r * 32 + lane];     // the row's sorted list, one entry per lane
       int li = l_idx[r * 32 + lane];
 #pragma unroll
@@ -209,22 +315,33 @@ __global__ void __launch_bounds__(kTtThreads, 1) topk_tc_candidates_kernel(const
         while (todo) {                     // ascending column index: an equal score stays behind
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
+#ifdef SPML_TT_TRACE
+          ++tt_events;
+#endif
+          // (the bar may have risen since the ballot: such a score finds pos == C and changes
+          // nothing; not re-checking it keeps the list's last entry off the dependent chain)
           const float sc = __shfl_sync(0xffffffffu, xs[j], src);
-          if (!(sc > thr)) continue;       // (the bar has risen since the ballot)
           const int pos = __popc(__ballot_sync(0xffffffffu, lane < C && lv >= sc));
           const float nv = __shfl_up_sync(0xffffffffu, lv, 1);
           const int ni = __shfl_up_sync(0xffffffffu, li, 1);
           if (lane > pos && lane < C) lv = nv, li = ni;
-          if (lane == pos) lv = sc, li = (int)(c0 + 32 * j + src);
-          thr = __shfl_sync(0xffffffffu, lv, C - 1);
+          if (lane == pos && lane < C) lv = sc, li = (int)(c0 + 32 * j + src);
         }
       }
+      thr = __shfl_sync(0xffffffffu, lv, C - 1);
       l_val[r * 32 + lane] = lv;
       l_idx[r * 32 + lane] = li;
       if (lane == 0) s_thr[r] = thr;
     }
+    TT_MARK(5);
     __syncthreads();   // the score tile and the operand tile are free again
+    TT_MARK(4);
   }
+#ifdef SPML_TT_TRACE
+  if (tid == 0 && blockIdx.x == 0 && (blockIdx.y == 0 || blockIdx.y == 7))
+    printf("topk_tc CTA(0,%d): loop top %lld split %lld mma %lld tmem->smem %lld rows (warp 0) %lld wait for the other warps %lld cycles; warp 0: %d row visits with work, %d insertions\n",
+           blockIdx.y, tt_t[0], tt_t[1], tt_t[2], tt_t[3], tt_t[5], tt_t[4], tt_visits, tt_events);
+#endif
 
   // ---- lists out: [row][slices][C]
   for (int i = tid; i < kTtRows * 32; i += kTtThreads) {
