@@ -121,13 +121,15 @@ int spml_normalize_pack_bwd(const float* de, const float* del, const float* e,
  *     zero vector) followed by the E-step (argmax of x.P^T, first index on
  *     ties).  Segment sums are accumulated in 64-bit fixed point (2^-32), so
  *     the result does not depend on the order of accumulation.
- *     The E-step runs as a TMA-fed tcgen05 GEMM (bf16 hi/lo split, near-ties
- *     re-scored in fp32) or as an fp32 CUDA-core GEMM; both return the same ids
+ *     The E-step runs as a tcgen05 GEMM (bf16 hi/lo split or, in the kernel that
+ *     keeps an image inside one thread-block cluster, a single fp16 product; near-ties
+ *     re-scored in fp32) or as an fp32 CUDA-core GEMM; all kernels return the same ids
  *     bit for bit (the choice is made per call from the shape).
  *     labels_out (int32) and labels_out_i64 (nullable) receive the final ids.
  *     workspace: spml_kmeans_workspace_bytes(batch, num_clusters, dim, iterations),
- *     16-byte aligned; the call is one cooperative launch (all its CTAs must be
- *     able to be resident: it waits for the SMs of concurrently running kernels).
+ *     16-byte aligned; the call is one launch: cooperative (all its CTAs must be
+ *     able to be resident: it waits for the SMs of concurrently running kernels) or
+ *     one cluster of up to 16 CTAs per image.
  */
 size_t spml_kmeans_workspace_bytes(int batch, int num_clusters, int dim, int iterations);
 int spml_kmeans(const float* x, const int32_t* img_off, int batch,
@@ -282,6 +284,11 @@ int spml_pack_tags(const int64_t* tags, int64_t rows, int cols, int64_t ld,
  *     qlab[q] == plab[index], hit_count[1] = number of queries that took part
  *     (accuracy = hit_count[0] / (hit_count[1] * k)).  qvalid / pvalid (nullable byte
  *     masks) drop query rows / prototype columns, for fixed-capacity buffers.
+ *     A large prototype bank without masks (retrieval inference,
+ *     predictions/segsort.py:68-125) runs on the tensor cores: tcgen05 scores select
+ *     k + 8 candidates per query, which are re-scored exactly; same results.  That
+ *     path keeps a scratch buffer per host thread and device (allocated on first use,
+ *     never while the stream is being captured: then the FMA kernel runs).
  */
 int spml_topk_ranking(const float* q, int64_t nq, const float* p, int64_t m, int dim,
                       const int64_t* qlab, const int64_t* plab, const uint8_t* qvalid,
