@@ -547,20 +547,21 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
             tc::tmem_ld_32x32(taddr + cb, v);
             tc::tmem_ld_wait();
             const int live = kb - cb;
-            if (slot >= 0) {
+            // candidates of this chunk as a bit mask (bitwise predicates and selects: branches
+            // inside the unrolled loop cost a convergence barrier each), then the few set bits
+            unsigned mc = 0;
 #pragma unroll
-              for (int u0 = 0; u0 < 32; u0 += 4) {
-                if (u0 < live) {
-#pragma unroll
-                  for (int u = u0; u < u0 + 4; ++u) {
-                    const float sc = __uint_as_float(v[u]);
-                    if (u < live && (sc >= thr || sc != sc)) {
-                      if (cnt < kKcCand) s_pk[slot * kKcCand + cnt] = cb + u;
-                      ++cnt;
-                    }
-                  }
-                }
-              }
+            for (int u = 0; u < 32; ++u) {
+              const float sc = __uint_as_float(v[u]);
+              mc |= ((sc >= thr) | (sc != sc)) ? (1u << u) : 0u;
+            }
+            if (live < 32) mc &= (1u << live) - 1u;
+            if (slot < 0) mc = 0;
+            while (mc) {
+              const int u = __ffs(mc) - 1;
+              mc &= mc - 1;
+              if (cnt < kKcCand) s_pk[slot * kKcCand + cnt] = cb + u;
+              ++cnt;
             }
           }
           if (amb) {

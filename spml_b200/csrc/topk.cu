@@ -197,7 +197,11 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
       for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+        {   // bitwise predicates + selects: the short-circuit form compiles to divergent branches
+          const bool take = (ov > bv) | ((ov == bv) & (oi < bi));
+          bv = take ? ov : bv;
+          bi = take ? oi : bi;
+        }
       }
       if (li[i][0] == bi) {  // the winner pops its head
 #pragma unroll
@@ -235,7 +239,11 @@ topk_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ p
         for (int o = 16; o > 0; o >>= 1) {
           const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
           const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+          {   // bitwise predicates + selects: the short-circuit form compiles to divergent branches
+          const bool take = (ov > bv) | ((ov == bv) & (oi < bi));
+          bv = take ? ov : bv;
+          bi = take ? oi : bi;
+        }
         }
         if (mi[0] == bi) {
 #pragma unroll

@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(256) topk_tc_merge_kernel(
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (ov > wv || (ov == wv && oi < wi)) wv = ov, wi = oi;
+      const bool take = (ov > wv) | ((ov == wv) & (oi < wi));
+      wv = take ? ov : wv;
+      wi = take ? oi : wi;
     }
     if (wi == 0x7fffffff) break;          // fewer than C prototypes in total
     if (bi == wi && bj >= 0) {            // the lane that owns the winner moves on
