@@ -365,6 +365,10 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
     max_ss = warp_sum(max_ss);
     if (lane == 0) atomicMax(&s_maxn, __float_as_int(max_ss));
   }
+  // the fp32 rows of the owned prototypes start as the zero vector (an empty cluster is never
+  // rebuilt, and the scratch holds whatever the last call left there)
+  for (int j = warp; rank + j * cs < kb; j += kKcWarps)
+    for (int d = lane; d < dim; d += 32) gpf[(rank + j * cs) * dim + d] = 0.f;
   if (__syncthreads_or(bad) && tid == 0) *p.poison = 1;
   // |score error| <= (2 u + u^2) |x| |p| + subnormal terms with u = 2^-11 (fp16), |p| <= 1, plus
   // the accumulation in the tensor core; a gap of twice that decides the label

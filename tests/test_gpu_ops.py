@@ -64,10 +64,42 @@ def test_nearest_prototype_ties(units):
   assert torch.equal(got, t['idx'])
 
 
-def test_kmeans_with_empty_cluster(units):
+@pytest.mark.parametrize('path', ['', 'cluster', 'small', 'tc', 'fp32'])
+def test_kmeans_with_empty_cluster(units, path, monkeypatch):
+  if path:
+    monkeypatch.setenv('SPML_B200_KMEANS', path)
   u = units['kmeans_empty']
   got = segsort_common.kmeans_with_initial_labels(cu(u['e']), cu(u['lab0']), 4, 10).cpu()
   assert torch.equal(got, u['lab'])
+
+
+@pytest.mark.parametrize('path', ['cluster', 'small', 'fp32'])
+def test_kmeans_empty_cluster_next_to_near_zero_scores(path, monkeypatch):
+  """An empty cluster is the zero vector (score exactly 0); pixels that are almost orthogonal to
+  every live prototype are ambiguous against it and go through the exact re-check, which must
+  see zeros for the empty cluster (the cluster kernel keeps those rows in a scratch that outlives
+  the call).  Every kernel against the oracle."""
+  monkeypatch.setenv('SPML_B200_KMEANS', path)
+  g = torch.Generator().manual_seed(3)
+  dim, k, n = 16, 6, 3000
+  e = torch.zeros(n, dim)
+  lab0 = torch.zeros(n, dtype=torch.long)
+  for c in range(3):                                   # three live clusters along axes 0..2
+    rows = slice(c * 900, (c + 1) * 900)
+    e[rows, c] = 1.0
+    e[rows] += 0.05 * torch.randn(900, dim, generator=g)
+    lab0[rows] = c
+  rest = slice(2700, n)                                # pixels in the orthogonal complement
+  e[rest, 8:] = torch.randn(n - 2700, dim - 8, generator=g)
+  e[rest, :3] = 1e-4 * torch.randn(n - 2700, 3, generator=g)
+  lab0[rest] = torch.randint(0, 3, (n - 2700,), generator=g)
+  e = O.l2_normalize(e)
+  # fill the scratch of an earlier call with other prototypes first
+  segsort_common.kmeans_with_initial_labels(cu(O.l2_normalize(torch.randn(n, dim, generator=g))),
+                                            cu(torch.randint(0, k, (n,), generator=g)), k, 3)
+  want = O.spherical_kmeans(e, lab0, k, 10)
+  got = segsort_common.kmeans_with_initial_labels(cu(e), cu(lab0), k, 10).cpu()
+  assert int((got != want).sum()) == 0
 
 
 @pytest.mark.parametrize('n,dim,k', [(5000, 66, 36), (3000, 37, 144), (4097, 130, 100)])
