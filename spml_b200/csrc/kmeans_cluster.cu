@@ -612,7 +612,10 @@ __global__ void __launch_bounds__(kKcThreads, 1) kmeans_cluster_kernel(const Kme
       }
       if (s_ndefer > 0) {
         // rows with many candidates (or more ambiguous rows than slots): every prototype, one
-        // warp per row, lanes across the prototypes
+        // warp per row, lanes across the prototypes.  (The barrier keeps the label stores just
+        // above apart from the scan for the 255 markers below: they never touch a marked row,
+        // but they are stores to the array this loop reads.)
+        __syncthreads();
         for (int r = warp; r < nrows; r += kKcWarps) {
           if (s_lab[r] != 255) continue;   // warp-uniform
           float bv = -INFINITY;
