@@ -34,6 +34,9 @@ __device__ __forceinline__ int64_t resolve_ignore(int64_t host_value, const int6
 // is 12 us for the 128 tiles of one 512 x 512 image; here a tile waits for the slowest of its
 // predecessors plus one L2 round trip.  Tiles take their number from a ticket, so every
 // predecessor is already running (or done) and publishes without waiting for anybody.
+// Cost: tile t reads t words, T^2 / 2 in total - 0.5 M words at batch 4 of 128 x 128 maps (1 024
+// tiles), nothing next to the embedding traffic; beyond ~10^4 tiles per call a windowed variant
+// that stops at the first published inclusive prefix would be the thing to write.
 __device__ __forceinline__ void publish_tile_count(unsigned long long* state, int tile, int total) {
   // one 64-bit word: flag and count arrive together
   reinterpret_cast<volatile unsigned long long*>(state)[tile] = (1ull << 32) | (unsigned)total;
