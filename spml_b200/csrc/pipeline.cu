@@ -11,6 +11,7 @@
 // the caller's stream, so the call is still "everything enqueued on `stream`" for the caller.
 #include <algorithm>
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ struct StreamPool {
   // straight into pinned host memory and the host polls `seq` (a 16-byte cudaMemcpyAsync into
   // pageable memory + synchronise costs ~10 us of copy-engine and driver latency on the one
   // host-device round trip of the step)
+  cudaEvent_t counts_ev;      // (blocking variant: the count copy has landed)
   int32_t* host_counts;       // pinned, mapped: 8 words
   int32_t* host_counts_dev;   // the same words as the device sees them
   int32_t seq;
@@ -55,6 +57,7 @@ static int get_pool(StreamPool** out) {
       SPML_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
     }
     SPML_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    SPML_CUDA(cudaEventCreateWithFlags(&p.counts_ev, cudaEventDisableTiming));
     SPML_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p.host_counts), 8 * sizeof(int32_t),
                             cudaHostAllocMapped));
     for (int i = 0; i < 8; ++i) p.host_counts[i] = 0;
@@ -598,14 +601,42 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
                           a->num_clusters, a->num_segments, a->label_divisor, a->sem_out, a->inst_out,
                           a->status, a->counts_host ? a->counts_dev : nullptr,
                           a->counts_host ? pool->host_counts_dev : nullptr, pool->seq, uq_ws, st));
+  // How the host waits for the counts.  Alone on the host it polls the pinned words (below).
+  // With several ranks per host (torchrun sets LOCAL_WORLD_SIZE / WORLD_SIZE) the polling thread
+  // was measured to cost a neighbouring rank up to ~100 us per step every other run (shared
+  // cores), so there the driver's own wait is used: a 16-byte copy into the caller's memory,
+  // which returns once the data is there.  SPML_B200_COUNT_WAIT=poll|block overrides.
+  static const bool poll_counts = []() {
+    const char* e = getenv("SPML_B200_COUNT_WAIT");
+    if (e && !strcmp(e, "poll")) return true;
+    if (e && !strcmp(e, "block")) return false;
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const char* w = getenv("WORLD_SIZE");
+    const int ranks = lw ? atoi(lw) : (w ? atoi(w) : 1);
+    return ranks <= 1;
+  }();
+  if (a->counts_host && !poll_counts) {
+    SPML_CUDA(cudaMemcpyAsync(a->counts_host, a->counts_dev, 4 * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, st));
+    SPML_CUDA(cudaEventRecord(pool->counts_ev, st));
+  }
   SPML_TRY(unique_finish(true, cap, rows_dev, 0, a->segment_ids, nullptr, nullptr, a->num_segments,
                          nullptr, uq_ws, st));
+  if (a->counts_host && !poll_counts) {
+    SPML_CUDA(cudaEventSynchronize(pool->counts_ev));
+    return SPML_OK;
+  }
   if (a->counts_host) {
-    // the step's one wait for the device: poll the sequence number; look at the stream now and
-    // then so that a failed kernel surfaces as an error instead of a hang
+    // the step's one wait for the device: poll the sequence number
     volatile int32_t* h = pool->host_counts;
     for (unsigned spins = 1; h[4] != pool->seq; ++spins) {
-      if ((spins & 0x3ffu) == 0) {
+      // PAUSE: a bare load loop starves the sibling hyper-thread; the stream is looked at every
+      // 65 536 polls (the query takes a driver lock) so that a failed kernel surfaces as an
+      // error instead of a hang
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      if ((spins & 0xffffu) == 0) {
         const cudaError_t q = cudaStreamQuery(st);
         if (q == cudaSuccess) {
           if (h[4] == pool->seq) break;
