@@ -43,6 +43,9 @@ struct StreamPool {
 // thread (lib/nn/parallel/data_parallel.py:105), so pools are never shared between threads
 // and an event is only ever re-recorded by the thread that waits on it.
 static thread_local StreamPool g_pools[kMaxDevices];
+// (host thread, device) pairs that drive this library in the process: more than one means the
+// reference's thread-per-GPU DataParallel, where the count read-back must not spin (below)
+static std::atomic<int> g_pool_count{0};
 
 static int get_pool(StreamPool** out) {
   int device = 0;
@@ -64,6 +67,7 @@ static int get_pool(StreamPool** out) {
     SPML_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.host_counts_dev), p.host_counts, 0));
     p.seq = 0;
     p.ready = true;
+    g_pool_count.fetch_add(1, std::memory_order_relaxed);
   }
   *out = &p;
   return SPML_OK;
@@ -605,7 +609,9 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
   // With several ranks per host (torchrun sets LOCAL_WORLD_SIZE / WORLD_SIZE) the polling thread
   // was measured to cost a neighbouring rank up to ~100 us per step every other run (shared
   // cores), so there the driver's own wait is used: a 16-byte copy into the caller's memory,
-  // which returns once the data is there.  SPML_B200_COUNT_WAIT=poll|block overrides.
+  // which returns once the data is there; likewise when several host threads of this process
+  // drive GPUs (thread-per-GPU DataParallel).  SPML_B200_COUNT_WAIT=poll|block overrides the
+  // rank heuristic.
   static const bool poll_counts = []() {
     const char* e = getenv("SPML_B200_COUNT_WAIT");
     if (e && !strcmp(e, "poll")) return true;
@@ -615,14 +621,15 @@ int spml_segment_by_kmeans(const spml_cluster_args* a, void* workspace, size_t w
     const int ranks = lw ? atoi(lw) : (w ? atoi(w) : 1);
     return ranks <= 1;
   }();
-  if (a->counts_host && !poll_counts) {
+  const bool poll = poll_counts && g_pool_count.load(std::memory_order_relaxed) <= 1;
+  if (a->counts_host && !poll) {
     SPML_CUDA(cudaMemcpyAsync(a->counts_host, a->counts_dev, 4 * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, st));
     SPML_CUDA(cudaEventRecord(pool->counts_ev, st));
   }
   SPML_TRY(unique_finish(true, cap, rows_dev, 0, a->segment_ids, nullptr, nullptr, a->num_segments,
                          nullptr, uq_ws, st));
-  if (a->counts_host && !poll_counts) {
+  if (a->counts_host && !poll) {
     SPML_CUDA(cudaEventSynchronize(pool->counts_ev));
     return SPML_OK;
   }
